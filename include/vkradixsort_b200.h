@@ -1,0 +1,157 @@
+/*
+ * vkradixsort_b200.h -- C-ABI of the B200-native (sm_100a) LSD radix sort that replaces
+ * the VkRadixSort compute dispatches.
+ *
+ * The reference has no FFI; its seam is the C++ pass surface
+ *   engine::MultiRadixSortPass  (multiradixsort/include/MultiRadixSortPass.h:7-40)
+ *   engine::SingleRadixSortPass (singleradixsort/include/SingleRadixSortPass.h:7-28)
+ * plus the buffer / push-constant / dispatch convention of README.md:200-241.  Each entry
+ * point below names the reference interface it stands in for.  The C++ facade that keeps the
+ * reference's class and member names on top of this ABI is include/vkradixsort_b200.hpp.
+ *
+ * Conventions
+ *  - Plain C: pointers and sizes only.  `stream` is a cudaStream_t passed as void*
+ *    (NULL = the legacy default stream).
+ *  - All device buffers are caller-owned (reference: Buffer objects owned by the caller,
+ *    multiradixsort/src/MultiRadixSort.cpp:83-95).  Nothing is allocated per call; the
+ *    handle owns a small workspace sized at vkrs_create() (grown, with a device sync, only
+ *    if a later call exceeds the hint).
+ *  - All work is enqueued on `stream`, no host synchronisation inside (reference: the caller
+ *    blocks with vkQueueWaitIdle, MultiRadixSort.cpp:62).  The *_host entry points are the
+ *    exception: they copy in, sort, copy out and return when the result is in host memory.
+ *  - Result lands in buffer 0; buffer 1 and the histogram buffer hold unspecified scratch on
+ *    return (README.md:132,241; MultiRadixSort.cpp:99).
+ *  - Return value: VKRS_OK or a negative vkrs_status; vkrs_last_error() gives the text.  No
+ *    C++ exception crosses this boundary (the facade turns failures back into
+ *    std::runtime_error as the reference throws, ComputePass.h:51-53).
+ *  - A handle is not thread-safe; distinct handles on distinct streams are independent.
+ */
+#ifndef VKRADIXSORT_B200_H
+#define VKRADIXSORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKRS_WORKGROUP_SIZE 256u  /* multi_radixsort.comp:11 */
+#define VKRS_RADIX_SORT_BINS 256u /* multi_radixsort.comp:12 */
+
+typedef enum vkrs_status {
+    VKRS_OK = 0,
+    VKRS_ERR_INVALID_ARGUMENT = -1,
+    VKRS_ERR_CUDA = -2,
+    VKRS_ERR_UNSUPPORTED = -3, /* e.g. N >= 2^30, the reference's own uint32 byte-size cap */
+    VKRS_ERR_INTERNAL = -4
+} vkrs_status;
+
+/* MultiRadixSortPass::PushConstantsHistograms / PushConstants
+ * (multiradixsort/include/MultiRadixSortPass.h:17-31; GLSL side multi_radixsort.comp:17-22).
+ * Same 16-byte layout; both reference structs are identical, so one type serves both. */
+typedef struct vkrs_multi_push_constants {
+    uint32_t g_num_elements;
+    uint32_t g_shift;
+    uint32_t g_num_workgroups;
+    uint32_t g_num_blocks_per_workgroup;
+} vkrs_multi_push_constants;
+
+/* SingleRadixSortPass::PushConstants (singleradixsort/include/SingleRadixSortPass.h:16-18). */
+typedef struct vkrs_single_push_constants {
+    uint32_t g_num_elements;
+} vkrs_single_push_constants;
+
+typedef struct vkrs_context *vkrs_handle;
+
+/* ---- lifecycle: Pass::create / Pass::release (engine/include/engine/passes/Pass.h:18-52) ----
+ * No run-time shader compilation: kernels are compiled ahead of time for sm_100a. */
+int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_hint);
+int vkrs_destroy(vkrs_handle handle);
+const char *vkrs_last_error(vkrs_handle handle); /* handle may be NULL: last create() error */
+const char *vkrs_version(void);
+
+/* ---- dispatch sizing: ComputePass::setGlobalInvocationSize / getWorkGroupCount
+ * (engine/include/engine/passes/ComputePass.h:16-29,58-60) with the global size of
+ * MultiRadixSort.cpp:13-15.  Pure host arithmetic. */
+uint32_t vkrs_global_invocation_size(uint32_t num_elements, uint32_t num_blocks_per_workgroup);
+uint32_t vkrs_workgroup_count(uint32_t global_invocation_size); /* ceil(gis / 256) */
+
+/* ---- per-stage entry points: the two dispatches of MultiRadixSortPass::recordCommands
+ * (multiradixsort/src/MultiRadixSortPass.cpp:10-20). ------------------------------------ */
+
+/* Stage RADIX_SORT_HISTOGRAMS = multi_radixsort_histograms.comp:31-56.
+ * histograms[256*w + b] = #{keys of workgroup w's slab with digit b}; every row is fully
+ * overwritten (no pre-zeroing needed).  histograms must hold g_num_workgroups*256 uint32. */
+int vkrs_multi_histograms(vkrs_handle handle, const uint32_t *elements_in, uint32_t *histograms,
+                          const vkrs_multi_push_constants *pc, void *stream);
+
+/* Stage RADIX_SORT = multi_radixsort.comp:45-127: offsets from the histogram matrix, then the
+ * stable rank + scatter of every workgroup slab.  values_* may be NULL (keys only, the
+ * reference's behaviour); when given, a uint32 payload travels with its key (config 3). */
+int vkrs_multi_scatter(vkrs_handle handle, const uint32_t *elements_in, uint32_t *elements_out,
+                       const uint32_t *histograms, const vkrs_multi_push_constants *pc,
+                       const uint32_t *values_in, uint32_t *values_out, void *stream);
+
+/* One MultiRadixSortPass::execute (ComputePass.h:31-56): both stages for the current g_shift. */
+int vkrs_multi_pass(vkrs_handle handle, const uint32_t *elements_in, uint32_t *elements_out,
+                    uint32_t *histograms, const vkrs_multi_push_constants *pc, void *stream);
+
+/* ---- whole sort: the timed loop of MultiRadixSort::execute (MultiRadixSort.cpp:49-62) -----
+ * Four 8-bit digit passes, buf0 -> buf1 -> buf0 -> buf1 -> buf0.  pc->g_shift is ignored
+ * (the loop sets 0,8,16,24, :57-58); g_num_workgroups / g_num_blocks_per_workgroup describe
+ * the caller's histogram buffer (capacity g_num_workgroups*256 uint32, may be NULL) and are
+ * otherwise only validated: this entry is free to use its own tiling (fused Onesweep
+ * schedule: one 4x256 histogram kernel + 4 single-pass chained-scan scatter kernels). */
+int vkrs_multi_sort(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
+                    const vkrs_multi_push_constants *pc, void *stream);
+
+/* Same with a uint32 payload per key (extension, BASELINE.json config 3): stable by key. */
+int vkrs_multi_sort_pairs(vkrs_handle handle, uint32_t *keys0, uint32_t *keys1, uint32_t *values0,
+                          uint32_t *values1, uint32_t *histograms, const vkrs_multi_push_constants *pc,
+                          void *stream);
+
+/* The reference's compile-time SORT_64BIT variant (MultiRadixSort.h:10-18; 8 iterations,
+ * MultiRadixSort.cpp:51-55). */
+int vkrs_multi_sort_u64(vkrs_handle handle, uint64_t *buf0, uint64_t *buf1, uint32_t *histograms,
+                        const vkrs_multi_push_constants *pc, void *stream);
+
+/* The reference loop run literally through the per-stage entry points (4 x histograms +
+ * scatter with the caller's tiling); kept so the staged path can be timed and compared. */
+int vkrs_multi_sort_staged(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
+                           const vkrs_multi_push_constants *pc, void *stream);
+
+/* ---- single-workgroup path: SingleRadixSortPass::execute with single_radixsort.comp:42-139
+ * (singleradixsort/src/SingleRadixSort.cpp:12-28).  One CTA, four passes, result in buf0. */
+int vkrs_single_sort(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1,
+                     const vkrs_single_push_constants *pc, void *stream);
+
+/* Size-based choice between the single and the multi path (README.md:18-21 leaves this to
+ * the user).  histograms may be NULL. */
+int vkrs_sort_auto(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t num_elements, void *stream);
+
+/* ---- host-buffer convenience = prepareBuffers + execute loop + verify's download
+ * (MultiRadixSort.cpp:83-102): H2D of host_keys (pinned or pageable), sort on the device in
+ * handle-owned buffers, D2H back into host_keys; returns after the data is back. */
+int vkrs_multi_sort_host(vkrs_handle handle, uint32_t *host_keys, uint32_t num_elements, void *stream);
+
+/* ---- device-side error flag (chained-scan look-back watchdog).  Synchronises `stream`,
+ * returns VKRS_ERR_INTERNAL if any kernel since the last check raised the flag. ---- */
+int vkrs_check_device_error(vkrs_handle handle, void *stream);
+
+/* ---- tuning hooks: pick one of the precompiled tile configurations of the fused keys-only
+ * pass kernel (also settable with the VKRS_VARIANT environment variable at create time). */
+int vkrs_num_variants(void);
+const char *vkrs_variant_name(int variant);
+int vkrs_set_variant(vkrs_handle handle, int variant);
+
+/* ---- introspection for tests / benches ---- */
+/* Number of kernel launches the handle has enqueued since creation. */
+uint64_t vkrs_launch_count(vkrs_handle handle);
+/* Tile size (keys per CTA step) of the fused multi path. */
+uint32_t vkrs_tile_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKRADIXSORT_B200_H */

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+
+    O.build()
+    return O
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """The product library must exist; build it if a fresh checkout has not yet."""
+    from vkradixsort_b200 import capi
+
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+
+        g.build()
+    return capi.load()

@@ -1,0 +1,94 @@
+"""CPU tests of the drop-in boundary: the library loads, exports every declared symbol, the host
+arithmetic matches the reference, and compute entry points fail loudly without a GPU (no CPU
+fallback exists)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_all_exported(built_lib):
+    from vkradixsort_b200 import capi
+
+    header = open(os.path.join(ROOT, "include", "vkradixsort_b200.h")).read()
+    declared = set(re.findall(r"\b(vkrs_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found in the header"
+    for name in sorted(declared):
+        assert hasattr(built_lib, name), f"{name} declared in include/vkradixsort_b200.h but not exported"
+    assert declared == set(capi.EXPORTED_SYMBOLS)
+
+
+def test_struct_layout_matches_reference():
+    from vkradixsort_b200 import capi
+
+    # MultiRadixSortPass.h:17-31: 4 x uint32, std430 => 16 bytes; SingleRadixSortPass.h:16-18: 4 bytes
+    assert ctypes.sizeof(capi.MultiPushConstants) == 16
+    assert [f[0] for f in capi.MultiPushConstants._fields_] == [
+        "g_num_elements", "g_shift", "g_num_workgroups", "g_num_blocks_per_workgroup"]
+    assert ctypes.sizeof(capi.SinglePushConstants) == 4
+
+
+def test_dispatch_sizing_matches_reference(built_lib, oracle):
+    from vkradixsort_b200 import capi
+
+    assert capi.global_invocation_size(1000000, 32) == 31250
+    assert capi.workgroup_count(31250) == 123  # README.md:261
+    for n in (0, 1, 31, 32, 33, 255, 256, 257, 1000, 10**6, 10**8, 8 * 10**8):
+        for nb in (1, 3, 32, 512, 4096):
+            gis = capi.global_invocation_size(n, nb)
+            assert gis == oracle.global_invocation_size(n, nb)
+            assert capi.workgroup_count(gis) == oracle.workgroup_count(n, nb)
+    pc = capi.multi_push_constants(10**8, 32)
+    assert (pc.g_num_elements, pc.g_num_workgroups, pc.g_num_blocks_per_workgroup) == (10**8, 12208, 32)
+
+
+def test_version_and_variants(built_lib):
+    from vkradixsort_b200 import capi
+
+    assert "sm_100a" in capi.version()
+    assert capi.num_variants() >= 1
+    assert capi.tile_size() % 256 == 0
+    assert all(capi.variant_name(v) for v in range(capi.num_variants()))
+
+
+def test_facade_sizing_without_gpu(built_lib):
+    from vkradixsort_b200 import GPUContext, MultiRadixSortPass
+
+    p = MultiRadixSortPass(GPUContext(0))
+    p.setGlobalInvocationSize(MultiRadixSortPass.RADIX_SORT_HISTOGRAMS, 31250, 1, 1)
+    p.setGlobalInvocationSize(MultiRadixSortPass.RADIX_SORT, 31250, 1, 1)
+    assert p.getWorkGroupCount(MultiRadixSortPass.RADIX_SORT).width == 123
+    ctx = GPUContext(0)
+    assert ctx.getActiveIndex() == 0
+    ctx.incrementActiveIndex()
+    assert ctx.getActiveIndex() == 1
+    ctx.incrementActiveIndex()
+    assert ctx.getActiveIndex() == 0
+    with pytest.raises(AssertionError):
+        p._bound(0, 0)  # unbound descriptor: the reference asserts (Pass.h:59-60)
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device create() must fail with a CUDA error, never silently compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; the loud-failure path is exercised on CPU-only boxes")
+    from vkradixsort_b200 import Handle, VkrsError, capi
+
+    with pytest.raises(VkrsError) as ei:
+        Handle(0)
+    assert ei.value.status == capi.VKRS_ERR_CUDA
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "vkradixsort_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (
+                    f"{os.path.join(dirpath, f)} mentions the oracle; the product path must not depend on it")

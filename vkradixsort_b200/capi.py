@@ -1,0 +1,252 @@
+"""ctypes binding of the C-ABI in include/vkradixsort_b200.h.
+
+The shared library (vkradixsort_b200/lib/libvkradixsort_b200.so, built by
+``__graft_entry__.build()`` / ``make -C vkradixsort_b200/csrc``) is the product; this module is
+only the thinnest possible way to reach it from Python tests and bench.py.  There is no CPU
+fallback: if the library is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvkradixsort_b200.so")
+
+VKRS_OK = 0
+VKRS_ERR_INVALID_ARGUMENT = -1
+VKRS_ERR_CUDA = -2
+VKRS_ERR_UNSUPPORTED = -3
+VKRS_ERR_INTERNAL = -4
+
+WORKGROUP_SIZE = 256
+RADIX_SORT_BINS = 256
+
+# Every symbol include/vkradixsort_b200.h declares (tests check that all of them are exported).
+EXPORTED_SYMBOLS = [
+    "vkrs_create", "vkrs_destroy", "vkrs_last_error", "vkrs_version",
+    "vkrs_global_invocation_size", "vkrs_workgroup_count",
+    "vkrs_multi_histograms", "vkrs_multi_scatter", "vkrs_multi_pass",
+    "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
+    "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host",
+    "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant",
+    "vkrs_launch_count", "vkrs_tile_size",
+]
+
+
+class MultiPushConstants(ctypes.Structure):
+    """vkrs_multi_push_constants == MultiRadixSortPass::PushConstants (MultiRadixSortPass.h:17-31)."""
+
+    _fields_ = [
+        ("g_num_elements", ctypes.c_uint32),
+        ("g_shift", ctypes.c_uint32),
+        ("g_num_workgroups", ctypes.c_uint32),
+        ("g_num_blocks_per_workgroup", ctypes.c_uint32),
+    ]
+
+
+class SinglePushConstants(ctypes.Structure):
+    """vkrs_single_push_constants == SingleRadixSortPass::PushConstants (SingleRadixSortPass.h:16-18)."""
+
+    _fields_ = [("g_num_elements", ctypes.c_uint32)]
+
+
+class VkrsError(RuntimeError):
+    """Raised for any non-zero status, as the reference throws std::runtime_error (ComputePass.h:51-53)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"vkrs status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C vkradixsort_b200/csrc`. There is no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u32, u64, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+    mpc, spc = ctypes.POINTER(MultiPushConstants), ctypes.POINTER(SinglePushConstants)
+    sig = {
+        "vkrs_create": (i32, [ctypes.POINTER(vp), i32, u64]),
+        "vkrs_destroy": (i32, [vp]),
+        "vkrs_last_error": (ctypes.c_char_p, [vp]),
+        "vkrs_version": (ctypes.c_char_p, []),
+        "vkrs_global_invocation_size": (u32, [u32, u32]),
+        "vkrs_workgroup_count": (u32, [u32]),
+        "vkrs_multi_histograms": (i32, [vp, vp, vp, mpc, vp]),
+        "vkrs_multi_scatter": (i32, [vp, vp, vp, vp, mpc, vp, vp, vp]),
+        "vkrs_multi_pass": (i32, [vp, vp, vp, vp, mpc, vp]),
+        "vkrs_multi_sort": (i32, [vp, vp, vp, vp, mpc, vp]),
+        "vkrs_multi_sort_pairs": (i32, [vp, vp, vp, vp, vp, vp, mpc, vp]),
+        "vkrs_multi_sort_u64": (i32, [vp, vp, vp, vp, mpc, vp]),
+        "vkrs_multi_sort_staged": (i32, [vp, vp, vp, vp, mpc, vp]),
+        "vkrs_single_sort": (i32, [vp, vp, vp, spc, vp]),
+        "vkrs_sort_auto": (i32, [vp, vp, vp, u32, vp]),
+        "vkrs_multi_sort_host": (i32, [vp, vp, u32, vp]),
+        "vkrs_check_device_error": (i32, [vp, vp]),
+        "vkrs_num_variants": (i32, []),
+        "vkrs_variant_name": (ctypes.c_char_p, [i32]),
+        "vkrs_set_variant": (i32, [vp, i32]),
+        "vkrs_launch_count": (u64, [vp]),
+        "vkrs_tile_size": (u32, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(x) -> int | None:
+    """Device/host address of a torch tensor, numpy array, int or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):
+        return x.ctypes.data
+    raise TypeError(f"cannot take the address of {type(x)}")
+
+
+def _stream(stream) -> int | None:
+    if stream is None:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                return torch.cuda.current_stream().cuda_stream or None
+        except ImportError:
+            pass
+        return None
+    if isinstance(stream, int):
+        return stream or None
+    return stream.cuda_stream or None
+
+
+def global_invocation_size(num_elements: int, nb: int) -> int:
+    return int(load().vkrs_global_invocation_size(num_elements, nb))
+
+
+def workgroup_count(global_invocation_size_: int) -> int:
+    return int(load().vkrs_workgroup_count(global_invocation_size_))
+
+
+def multi_push_constants(num_elements: int, nb: int = 32, shift: int = 0) -> MultiPushConstants:
+    """Sizing exactly as MultiRadixSort::execute does it (MultiRadixSort.cpp:12-27)."""
+    W = workgroup_count(global_invocation_size(num_elements, nb))
+    return MultiPushConstants(num_elements, shift, W, nb)
+
+
+class Handle:
+    """Owns one vkrs_handle (Pass::create / Pass::release)."""
+
+    def __init__(self, device: int = 0, max_num_elements_hint: int = 0):
+        self._lib = load()
+        h = ctypes.c_void_p()
+        st = self._lib.vkrs_create(ctypes.byref(h), device, max_num_elements_hint)
+        if st != VKRS_OK:
+            raise VkrsError(st, (self._lib.vkrs_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vkrs_destroy(self._h)
+            self._h = None
+
+    release = close  # reference name: Pass::release
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, st: int):
+        if st != VKRS_OK:
+            raise VkrsError(st, (self._lib.vkrs_last_error(self._h) or b"").decode())
+
+    # ---- per stage ----
+    def multi_histograms(self, elements_in, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_histograms(self._h, _ptr(elements_in), _ptr(histograms), ctypes.byref(pc),
+                                                    _stream(stream)))
+
+    def multi_scatter(self, elements_in, elements_out, histograms, pc: MultiPushConstants, values_in=None,
+                      values_out=None, stream=None):
+        self._check(self._lib.vkrs_multi_scatter(self._h, _ptr(elements_in), _ptr(elements_out), _ptr(histograms),
+                                                 ctypes.byref(pc), _ptr(values_in), _ptr(values_out),
+                                                 _stream(stream)))
+
+    def multi_pass(self, elements_in, elements_out, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_pass(self._h, _ptr(elements_in), _ptr(elements_out), _ptr(histograms),
+                                              ctypes.byref(pc), _stream(stream)))
+
+    # ---- whole sorts ----
+    def multi_sort(self, buf0, buf1, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_sort(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms), ctypes.byref(pc),
+                                              _stream(stream)))
+
+    def multi_sort_pairs(self, keys0, keys1, values0, values1, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_sort_pairs(self._h, _ptr(keys0), _ptr(keys1), _ptr(values0), _ptr(values1),
+                                                    _ptr(histograms), ctypes.byref(pc), _stream(stream)))
+
+    def multi_sort_u64(self, buf0, buf1, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_sort_u64(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms),
+                                                  ctypes.byref(pc), _stream(stream)))
+
+    def multi_sort_staged(self, buf0, buf1, histograms, pc: MultiPushConstants, stream=None):
+        self._check(self._lib.vkrs_multi_sort_staged(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms),
+                                                     ctypes.byref(pc), _stream(stream)))
+
+    def single_sort(self, buf0, buf1, pc: SinglePushConstants, stream=None):
+        self._check(self._lib.vkrs_single_sort(self._h, _ptr(buf0), _ptr(buf1), ctypes.byref(pc), _stream(stream)))
+
+    def sort_auto(self, buf0, buf1, num_elements: int, stream=None):
+        self._check(self._lib.vkrs_sort_auto(self._h, _ptr(buf0), _ptr(buf1), num_elements, _stream(stream)))
+
+    def multi_sort_host(self, host_keys, num_elements: int, stream=None):
+        self._check(self._lib.vkrs_multi_sort_host(self._h, _ptr(host_keys), num_elements, _stream(stream)))
+
+    # ---- misc ----
+    def check_device_error(self, stream=None):
+        self._check(self._lib.vkrs_check_device_error(self._h, _stream(stream)))
+
+    def set_variant(self, variant: int):
+        self._check(self._lib.vkrs_set_variant(self._h, variant))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.vkrs_launch_count(self._h))
+
+
+def num_variants() -> int:
+    return int(load().vkrs_num_variants())
+
+
+def variant_name(v: int) -> str:
+    return (load().vkrs_variant_name(v) or b"").decode()
+
+
+def tile_size() -> int:
+    return int(load().vkrs_tile_size())
+
+
+def version() -> str:
+    return load().vkrs_version().decode()

@@ -1,0 +1,580 @@
+// vkrs_api.cu -- host side of the C-ABI declared in include/vkradixsort_b200.h.
+//
+// This file owns launch configuration, the handle's workspace and argument checking; it
+// contains no sorting logic and no CPU fallback: every entry point either enqueues the
+// sm_100a kernels of vkrs_kernels.cuh or returns an error.
+#include "../../include/vkradixsort_b200.h"
+#include "vkrs_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace {
+
+using namespace vkrs;
+
+// ---- fused-path kernel configurations (selectable for tuning runs) ----------------------
+struct PassConfig {
+    const char *name;
+    int threads, kpt, min_blocks;
+};
+
+constexpr int NUM_VARIANTS = 8;
+// Keep in sync with launch_pass_u32() below.
+const PassConfig kVariants[NUM_VARIANTS] = {
+    {"512x16 ballot", 512, 16, 2}, {"512x16 match.any", 512, 16, 2}, {"256x16 ballot", 256, 16, 4},
+    {"256x16 match.any", 256, 16, 4}, {"384x20 ballot", 384, 20, 2}, {"512x12 ballot", 512, 12, 2},
+    {"256x24 ballot", 256, 24, 3},   {"1024x8 ballot", 1024, 8, 1},
+};
+constexpr int DEFAULT_VARIANT = 0;
+
+// default configurations of the other paths
+constexpr int PAIR_THREADS = 512, PAIR_KPT = 12;
+constexpr int U64_THREADS = 512, U64_KPT = 8;
+constexpr int STAGED_THREADS = 256, STAGED_KPT = 16;
+constexpr int SINGLE_THREADS = 1024, SINGLE_KPT = 8;
+constexpr uint32_t AUTO_SINGLE_MAX = 4096; // vkrs_sort_auto: single path up to here (tuned on B200)
+
+thread_local std::string g_create_error;
+
+} // namespace
+
+struct vkrs_context {
+    int device = 0;
+    int sm_count = 148;
+    int variant = DEFAULT_VARIANT;
+    uint64_t launches = 0;
+    std::string error;
+
+    // control block: [8][256] global histograms | 8 tickets | done counter | error flag
+    uint32_t *ctrl = nullptr;
+    static constexpr size_t CTRL_HIST = 8 * 256;
+    static constexpr size_t CTRL_TICKETS = CTRL_HIST;
+    static constexpr size_t CTRL_DONE = CTRL_HIST + 8;
+    static constexpr size_t CTRL_ERROR = CTRL_HIST + 9;
+    static constexpr size_t CTRL_WORDS = CTRL_HIST + 16;
+
+    // chained-scan tile status, two arrays used alternately by consecutive passes
+    uint32_t *status[2] = {nullptr, nullptr};
+    uint64_t status_rows = 0;
+
+    // staged path: offsets[W][256], chunk sums, bin starts
+    uint32_t *staged_offsets = nullptr;
+    uint64_t staged_rows = 0;
+    uint32_t *staged_chunks = nullptr;
+    uint64_t staged_chunk_rows = 0;
+    uint32_t *staged_bin_start = nullptr;
+
+    // vkrs_multi_sort_host device buffers
+    uint32_t *host_buf[2] = {nullptr, nullptr};
+    uint64_t host_cap = 0;
+};
+
+namespace {
+
+int fail(vkrs_context *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->error = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define VKRS_CUDA(h, expr)                                                                                     \
+    do {                                                                                                       \
+        cudaError_t e__ = (expr);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return fail(h, VKRS_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__,   \
+                        __LINE__);                                                                             \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool active = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) {
+            cudaSetDevice(dev);
+            active = true;
+        }
+    }
+    ~DeviceGuard() {
+        if (active) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int grow(vkrs_context *h, T *&ptr, uint64_t &cap, uint64_t want, size_t elem_bytes, bool zero) {
+    if (want <= cap && ptr) return VKRS_OK;
+    // Growing is the one place a call may synchronise: the old workspace can still be in use.
+    VKRS_CUDA(h, cudaDeviceSynchronize());
+    if (ptr) VKRS_CUDA(h, cudaFree(ptr));
+    ptr = nullptr;
+    cap = 0;
+    void *p = nullptr;
+    VKRS_CUDA(h, cudaMalloc(&p, want * elem_bytes));
+    if (zero) VKRS_CUDA(h, cudaMemset(p, 0, want * elem_bytes));
+    ptr = static_cast<T *>(p);
+    cap = want;
+    return VKRS_OK;
+}
+
+int ensure_status(vkrs_context *h, uint64_t tiles) {
+    if (tiles <= h->status_rows) return VKRS_OK;
+    const uint64_t want = tiles + tiles / 8 + 64;
+    uint64_t c0 = h->status_rows, c1 = h->status_rows;
+    int r = grow(h, h->status[0], c0, want * RADIX, sizeof(uint32_t), true);
+    if (r) return r;
+    r = grow(h, h->status[1], c1, want * RADIX, sizeof(uint32_t), true);
+    if (r) return r;
+    h->status_rows = want;
+    return VKRS_OK;
+}
+
+template <typename Kernel>
+int set_smem(vkrs_context *h, Kernel kernel, size_t bytes) {
+    VKRS_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+    return VKRS_OK;
+}
+
+template <typename KeyT, bool HAS_VALUES, int THREADS, int KPT, int MATCH, int MIN_BLOCKS>
+int launch_pass_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                  uint32_t shift, int pass_index, cudaStream_t stream) {
+    using Sorter = TileSorter<KeyT, HAS_VALUES, THREADS, KPT, MATCH>;
+    auto kernel = onesweep_pass_kernel<KeyT, HAS_VALUES, THREADS, KPT, MATCH, MIN_BLOCKS>;
+    static thread_local int configured_device = -1;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, sizeof(typename Sorter::Smem));
+        if (r) return r;
+        configured_device = h->device;
+    }
+    const uint32_t tiles = (uint32_t) (((uint64_t) n + Sorter::TILE - 1) / Sorter::TILE);
+    kernel<<<tiles, THREADS, sizeof(typename Sorter::Smem), stream>>>(
+        in, out, vin, vout, n, shift, h->ctrl + pass_index * RADIX, h->status[pass_index & 1],
+        h->status[(pass_index + 1) & 1], h->ctrl + vkrs_context::CTRL_TICKETS + pass_index,
+        h->ctrl + vkrs_context::CTRL_ERROR);
+    h->launches++;
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t shift, int pass_index,
+                    cudaStream_t stream) {
+    switch (h->variant) {
+        case 0: return launch_pass_t<uint32_t, false, 512, 16, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 1: return launch_pass_t<uint32_t, false, 512, 16, MATCH_HW, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 2: return launch_pass_t<uint32_t, false, 256, 16, MATCH_BALLOT, 4>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 3: return launch_pass_t<uint32_t, false, 256, 16, MATCH_HW, 4>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 4: return launch_pass_t<uint32_t, false, 384, 20, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 5: return launch_pass_t<uint32_t, false, 512, 12, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 6: return launch_pass_t<uint32_t, false, 256, 24, MATCH_BALLOT, 3>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 7: return launch_pass_t<uint32_t, false, 1024, 8, MATCH_BALLOT, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", h->variant);
+    }
+}
+
+uint32_t variant_tile(int v) { return (uint32_t) (kVariants[v].threads * kVariants[v].kpt); }
+
+// Zero the control block and build the exclusive-scanned global histograms.
+template <typename KeyT, int NUM_PASSES>
+int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaStream_t stream) {
+    auto kernel = global_histogram_kernel<KeyT, NUM_PASSES>;
+    const size_t smem = (size_t) NUM_PASSES * 128 * 32 * sizeof(uint32_t);
+    static thread_local int configured_device = -1;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, smem);
+        if (r) return r;
+        configured_device = h->device;
+    }
+    VKRS_CUDA(h, cudaMemsetAsync(h->ctrl, 0, (vkrs_context::CTRL_DONE + 1) * sizeof(uint32_t), stream));
+    const int ctas_per_sm = (NUM_PASSES <= 4) ? 3 : 1;
+    uint64_t grid = (uint64_t) h->sm_count * ctas_per_sm;
+    const uint64_t min_grid = ((uint64_t) n + HIST_MAX_KEYS_PER_CTA - 1) / HIST_MAX_KEYS_PER_CTA;
+    if (grid < min_grid) grid = min_grid;
+    // per-CTA chunk: multiple of 2048 keys so that every CTA but the last starts 16-byte aligned
+    uint64_t per_cta = ((uint64_t) n + grid - 1) / grid;
+    per_cta = (per_cta + 2047) / 2048 * 2048;
+    if (per_cta == 0) per_cta = 2048;
+    grid = ((uint64_t) n + per_cta - 1) / per_cta;
+    if (grid == 0) grid = 1;
+    kernel<<<(unsigned) grid, HIST_THREADS, smem, stream>>>(keys, n, (uint32_t) per_cta, h->ctrl,
+                                                             h->ctrl + vkrs_context::CTRL_DONE);
+    h->launches++;
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int check_multi_pc(vkrs_context *h, const vkrs_multi_push_constants *pc, bool need_tiling) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!pc) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "push constants are NULL");
+    if (pc->g_num_elements >= (1u << 30))
+        return fail(h, VKRS_ERR_UNSUPPORTED, "g_num_elements=%u: at most 2^30-1 keys per call", pc->g_num_elements);
+    if (need_tiling) {
+        if (pc->g_shift > 31) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "g_shift=%u out of range", pc->g_shift);
+        if (pc->g_num_elements > 0) {
+            if (pc->g_num_blocks_per_workgroup == 0 || pc->g_num_workgroups == 0)
+                return fail(h, VKRS_ERR_INVALID_ARGUMENT, "g_num_workgroups / g_num_blocks_per_workgroup must be > 0");
+            const uint64_t covered = (uint64_t) pc->g_num_workgroups * pc->g_num_blocks_per_workgroup * 256ull;
+            if (covered < pc->g_num_elements)
+                return fail(h, VKRS_ERR_INVALID_ARGUMENT,
+                            "tiling covers %llu keys < g_num_elements=%u (W=%u, nb=%u)", (unsigned long long) covered,
+                            pc->g_num_elements, pc->g_num_workgroups, pc->g_num_blocks_per_workgroup);
+        }
+    }
+    return VKRS_OK;
+}
+
+int staged_histograms(vkrs_context *h, const uint32_t *in, uint32_t *hist, const vkrs_multi_push_constants *pc,
+                      cudaStream_t stream) {
+    staged_histograms_kernel<<<pc->g_num_workgroups, STAGED_HIST_THREADS, 0, stream>>>(
+        in, hist, pc->g_num_elements, pc->g_shift, pc->g_num_blocks_per_workgroup);
+    h->launches++;
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int staged_scatter(vkrs_context *h, const uint32_t *in, uint32_t *out, const uint32_t *hist,
+                   const vkrs_multi_push_constants *pc, const uint32_t *vin, uint32_t *vout, cudaStream_t stream) {
+    const uint32_t W = pc->g_num_workgroups;
+    const uint32_t chunks = (W + STAGED_CHUNK_ROWS - 1) / STAGED_CHUNK_ROWS;
+    int r = grow(h, h->staged_offsets, h->staged_rows, (uint64_t) W, RADIX * sizeof(uint32_t), false);
+    if (r) return r;
+    r = grow(h, h->staged_chunks, h->staged_chunk_rows, (uint64_t) chunks, RADIX * sizeof(uint32_t), false);
+    if (r) return r;
+    staged_colsum_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks);
+    staged_chunkscan_kernel<<<1, 256, 0, stream>>>(h->staged_chunks, chunks, h->staged_bin_start);
+    staged_offsets_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks, h->staged_bin_start,
+                                                     h->staged_offsets);
+    h->launches += 3;
+    VKRS_CUDA(h, cudaGetLastError());
+
+    if (vin) {
+        using Sorter = TileSorter<uint32_t, true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT>;
+        auto kernel = staged_scatter_kernel<true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT, 3>;
+        static thread_local int configured_device = -1;
+        if (configured_device != h->device) {
+            r = set_smem(h, kernel, sizeof(Sorter::Smem));
+            if (r) return r;
+            configured_device = h->device;
+        }
+        kernel<<<W, STAGED_THREADS, sizeof(Sorter::Smem), stream>>>(in, out, vin, vout, h->staged_offsets,
+                                                                    pc->g_num_elements, pc->g_shift,
+                                                                    pc->g_num_blocks_per_workgroup);
+    } else {
+        using Sorter = TileSorter<uint32_t, false, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT>;
+        auto kernel = staged_scatter_kernel<false, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT, 4>;
+        static thread_local int configured_device = -1;
+        if (configured_device != h->device) {
+            r = set_smem(h, kernel, sizeof(Sorter::Smem));
+            if (r) return r;
+            configured_device = h->device;
+        }
+        kernel<<<W, STAGED_THREADS, sizeof(Sorter::Smem), stream>>>(in, out, nullptr, nullptr, h->staged_offsets,
+                                                                    pc->g_num_elements, pc->g_shift,
+                                                                    pc->g_num_blocks_per_workgroup);
+    }
+    h->launches++;
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *vkrs_version(void) { return "vkradixsort_b200 0.1 (sm_100a)"; }
+
+uint32_t vkrs_tile_size(void) { return variant_tile(DEFAULT_VARIANT); }
+
+uint32_t vkrs_global_invocation_size(uint32_t num_elements, uint32_t nb) {
+    if (nb == 0) return 0;
+    uint32_t gis = num_elements / nb; // MultiRadixSort.cpp:13-15
+    if (num_elements % nb > 0) gis += 1;
+    return gis;
+}
+
+uint32_t vkrs_workgroup_count(uint32_t global_invocation_size) {
+    return (uint32_t) (((uint64_t) global_invocation_size + VKRS_WORKGROUP_SIZE - 1) / VKRS_WORKGROUP_SIZE); // ComputePass.h:24-29
+}
+
+int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_hint) {
+    if (!out_handle) return fail(nullptr, VKRS_ERR_INVALID_ARGUMENT, "out_handle is NULL");
+    *out_handle = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, VKRS_ERR_CUDA, "no CUDA device available: %s",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return fail(nullptr, VKRS_ERR_INVALID_ARGUMENT, "device %d out of range (0..%d)", device, count - 1);
+    DeviceGuard guard(device);
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, VKRS_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, VKRS_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    vkrs_context *h = new vkrs_context();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    if (const char *v = getenv("VKRS_VARIANT")) {
+        int iv = atoi(v);
+        if (iv >= 0 && iv < NUM_VARIANTS) h->variant = iv;
+    }
+    void *p = nullptr;
+    e = cudaMalloc(&p, vkrs_context::CTRL_WORDS * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(p, 0, vkrs_context::CTRL_WORDS * sizeof(uint32_t));
+    if (e == cudaSuccess) {
+        h->ctrl = static_cast<uint32_t *>(p);
+        e = cudaMalloc(&p, RADIX * sizeof(uint32_t));
+        if (e == cudaSuccess) h->staged_bin_start = static_cast<uint32_t *>(p);
+    }
+    if (e != cudaSuccess) {
+        int r = fail(nullptr, VKRS_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e));
+        vkrs_destroy(h);
+        return r;
+    }
+    if (max_num_elements_hint > 0) {
+        // smallest tile of any variant => most rows
+        const uint64_t tiles = (max_num_elements_hint + 4095) / 4096;
+        int r = ensure_status(h, tiles);
+        if (r) {
+            g_create_error = h->error;
+            vkrs_destroy(h);
+            return r;
+        }
+    }
+    *out_handle = h;
+    return VKRS_OK;
+}
+
+int vkrs_destroy(vkrs_handle h) {
+    if (!h) return VKRS_OK;
+    DeviceGuard guard(h->device);
+    cudaDeviceSynchronize();
+    cudaFree(h->ctrl);
+    cudaFree(h->status[0]);
+    cudaFree(h->status[1]);
+    cudaFree(h->staged_offsets);
+    cudaFree(h->staged_chunks);
+    cudaFree(h->staged_bin_start);
+    cudaFree(h->host_buf[0]);
+    cudaFree(h->host_buf[1]);
+    delete h;
+    return VKRS_OK;
+}
+
+const char *vkrs_last_error(vkrs_handle h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+uint64_t vkrs_launch_count(vkrs_handle h) { return h ? h->launches : 0; }
+
+int vkrs_set_variant(vkrs_handle h, int variant) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (variant < 0 || variant >= NUM_VARIANTS) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "variant %d out of range", variant);
+    h->variant = variant;
+    return VKRS_OK;
+}
+
+int vkrs_num_variants(void) { return NUM_VARIANTS; }
+
+const char *vkrs_variant_name(int variant) {
+    return (variant >= 0 && variant < NUM_VARIANTS) ? kVariants[variant].name : "";
+}
+
+// Reads (and clears) the device-side error flag; synchronises `stream`.
+int vkrs_check_device_error(vkrs_handle h, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    uint32_t flag = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VKRS_CUDA(h, cudaMemcpyAsync(&flag, h->ctrl + vkrs_context::CTRL_ERROR, sizeof flag, cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaStreamSynchronize(s));
+    if (flag != DEVERR_NONE) {
+        cudaMemsetAsync(h->ctrl + vkrs_context::CTRL_ERROR, 0, sizeof(uint32_t), s);
+        // tile status may be inconsistent after an aborted look-back: start clean
+        if (h->status[0]) cudaMemsetAsync(h->status[0], 0, h->status_rows * RADIX * sizeof(uint32_t), s);
+        if (h->status[1]) cudaMemsetAsync(h->status[1], 0, h->status_rows * RADIX * sizeof(uint32_t), s);
+        cudaStreamSynchronize(s);
+        return fail(h, VKRS_ERR_INTERNAL, "device error flag %u (1 = chained-scan look-back timed out)", flag);
+    }
+    return VKRS_OK;
+}
+
+int vkrs_multi_histograms(vkrs_handle h, const uint32_t *elements_in, uint32_t *histograms,
+                          const vkrs_multi_push_constants *pc, void *stream) {
+    int r = check_multi_pc(h, pc, true);
+    if (r) return r;
+    if (pc->g_num_elements == 0 && pc->g_num_workgroups == 0) return VKRS_OK; // zero-size dispatch
+    if (!histograms || (!elements_in && pc->g_num_elements > 0)) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    return staged_histograms(h, elements_in, histograms, pc, static_cast<cudaStream_t>(stream));
+}
+
+int vkrs_multi_scatter(vkrs_handle h, const uint32_t *elements_in, uint32_t *elements_out, const uint32_t *histograms,
+                       const vkrs_multi_push_constants *pc, const uint32_t *values_in, uint32_t *values_out,
+                       void *stream) {
+    int r = check_multi_pc(h, pc, true);
+    if (r) return r;
+    if (pc->g_num_elements == 0) return VKRS_OK;
+    if (!elements_in || !elements_out || !histograms) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if ((values_in == nullptr) != (values_out == nullptr))
+        return fail(h, VKRS_ERR_INVALID_ARGUMENT, "values_in and values_out must both be given or both be NULL");
+    DeviceGuard guard(h->device);
+    return staged_scatter(h, elements_in, elements_out, histograms, pc, values_in, values_out,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int vkrs_multi_pass(vkrs_handle h, const uint32_t *elements_in, uint32_t *elements_out, uint32_t *histograms,
+                    const vkrs_multi_push_constants *pc, void *stream) {
+    int r = vkrs_multi_histograms(h, elements_in, histograms, pc, stream);
+    if (r) return r;
+    return vkrs_multi_scatter(h, elements_in, elements_out, histograms, pc, nullptr, nullptr, stream);
+}
+
+int vkrs_multi_sort_staged(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
+                           const vkrs_multi_push_constants *pc_in, void *stream) {
+    int r = check_multi_pc(h, pc_in, false);
+    if (r) return r;
+    vkrs_multi_push_constants pc = *pc_in;
+    for (uint32_t i = 0; i < 4; ++i) { // MultiRadixSort.cpp:56-61
+        pc.g_shift = 8 * i;
+        uint32_t *in = (i & 1) ? buf1 : buf0, *out = (i & 1) ? buf0 : buf1;
+        r = vkrs_multi_pass(h, in, out, histograms, &pc, stream);
+        if (r) return r;
+    }
+    return VKRS_OK;
+}
+
+int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
+                    const vkrs_multi_push_constants *pc, void *stream) {
+    (void) histograms; // the fused schedule keeps its tile status in the handle's workspace
+    int r = check_multi_pc(h, pc, false);
+    if (r) return r;
+    const uint32_t n = pc->g_num_elements;
+    if (n == 0) return VKRS_OK;
+    if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t tile = variant_tile(h->variant);
+    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
+    if (r) return r;
+    r = launch_global_histogram<uint32_t, 4>(h, buf0, n, s);
+    if (r) return r;
+    for (int p = 0; p < 4; ++p) {
+        uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
+        r = launch_pass_u32(h, in, out, n, 8 * p, p, s);
+        if (r) return r;
+    }
+    return VKRS_OK;
+}
+
+int vkrs_multi_sort_pairs(vkrs_handle h, uint32_t *keys0, uint32_t *keys1, uint32_t *values0, uint32_t *values1,
+                          uint32_t *histograms, const vkrs_multi_push_constants *pc, void *stream) {
+    (void) histograms;
+    int r = check_multi_pc(h, pc, false);
+    if (r) return r;
+    const uint32_t n = pc->g_num_elements;
+    if (n == 0) return VKRS_OK;
+    if (!keys0 || !keys1 || !values0 || !values1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    constexpr uint32_t tile = PAIR_THREADS * PAIR_KPT;
+    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
+    if (r) return r;
+    r = launch_global_histogram<uint32_t, 4>(h, keys0, n, s);
+    if (r) return r;
+    for (int p = 0; p < 4; ++p) {
+        uint32_t *in = (p & 1) ? keys1 : keys0, *out = (p & 1) ? keys0 : keys1;
+        uint32_t *vin = (p & 1) ? values1 : values0, *vout = (p & 1) ? values0 : values1;
+        r = launch_pass_t<uint32_t, true, PAIR_THREADS, PAIR_KPT, MATCH_BALLOT, 2>(h, in, out, vin, vout, n, 8 * p, p, s);
+        if (r) return r;
+    }
+    return VKRS_OK;
+}
+
+int vkrs_multi_sort_u64(vkrs_handle h, uint64_t *buf0, uint64_t *buf1, uint32_t *histograms,
+                        const vkrs_multi_push_constants *pc, void *stream) {
+    (void) histograms;
+    int r = check_multi_pc(h, pc, false);
+    if (r) return r;
+    const uint32_t n = pc->g_num_elements;
+    if (n == 0) return VKRS_OK;
+    if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    constexpr uint32_t tile = U64_THREADS * U64_KPT;
+    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
+    if (r) return r;
+    using K = unsigned long long;
+    r = launch_global_histogram<K, 8>(h, reinterpret_cast<const K *>(buf0), n, s);
+    if (r) return r;
+    for (int p = 0; p < 8; ++p) { // NUM_ITERATIONS = 8, MultiRadixSort.cpp:54
+        K *in = reinterpret_cast<K *>((p & 1) ? buf1 : buf0), *out = reinterpret_cast<K *>((p & 1) ? buf0 : buf1);
+        r = launch_pass_t<K, false, U64_THREADS, U64_KPT, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, 8 * p, p, s);
+        if (r) return r;
+    }
+    return VKRS_OK;
+}
+
+int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_single_push_constants *pc,
+                     void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!pc) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "push constants are NULL");
+    const uint32_t n = pc->g_num_elements;
+    if (n == 0) return VKRS_OK;
+    if (n >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "g_num_elements=%u: at most 2^30-1 keys per call", n);
+    if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    using Sorter = TileSorter<uint32_t, false, SINGLE_THREADS, SINGLE_KPT, MATCH_BALLOT>;
+    auto kernel = single_sort_kernel<SINGLE_THREADS, SINGLE_KPT, MATCH_BALLOT>;
+    static thread_local int configured_device = -1;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, sizeof(Sorter::Smem));
+        if (r) return r;
+        configured_device = h->device;
+    }
+    kernel<<<1, SINGLE_THREADS, sizeof(Sorter::Smem), static_cast<cudaStream_t>(stream)>>>(buf0, buf1, n);
+    h->launches++;
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int vkrs_sort_auto(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t num_elements, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (num_elements <= AUTO_SINGLE_MAX) {
+        vkrs_single_push_constants pc{num_elements};
+        return vkrs_single_sort(h, buf0, buf1, &pc, stream);
+    }
+    vkrs_multi_push_constants pc{num_elements, 0, 0, 0};
+    return vkrs_multi_sort(h, buf0, buf1, nullptr, &pc, stream);
+}
+
+int vkrs_multi_sort_host(vkrs_handle h, uint32_t *host_keys, uint32_t num_elements, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (num_elements == 0) return VKRS_OK;
+    if (!host_keys) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "host_keys is NULL");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (num_elements > h->host_cap) {
+        uint64_t c0 = h->host_cap, c1 = h->host_cap;
+        int r = grow(h, h->host_buf[0], c0, num_elements, sizeof(uint32_t), false);
+        if (r) return r;
+        r = grow(h, h->host_buf[1], c1, num_elements, sizeof(uint32_t), false);
+        if (r) return r;
+        h->host_cap = num_elements;
+    }
+    const size_t bytes = (size_t) num_elements * sizeof(uint32_t);
+    VKRS_CUDA(h, cudaMemcpyAsync(h->host_buf[0], host_keys, bytes, cudaMemcpyHostToDevice, s));
+    int r = vkrs_sort_auto(h, h->host_buf[0], h->host_buf[1], num_elements, stream);
+    if (r) return r;
+    VKRS_CUDA(h, cudaMemcpyAsync(host_keys, h->host_buf[0], bytes, cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaStreamSynchronize(s));
+    return VKRS_OK;
+}
+
+} // extern "C"
