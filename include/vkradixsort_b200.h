@@ -144,6 +144,16 @@ int vkrs_check_device_error(vkrs_handle handle, void *stream);
 int vkrs_num_variants(void);
 const char *vkrs_variant_name(int variant);
 int vkrs_set_variant(vkrs_handle handle, int variant);
+int vkrs_get_variant(vkrs_handle handle);
+
+/* ---- opt-in per-kernel timing (the reference only has a wall clock around the loop,
+ * MultiRadixSort.cpp:49,63-65).  While enabled every kernel launch is bracketed by a CUDA event
+ * pair on its stream.  vkrs_profile_collect() synchronises the device, folds the pairs into
+ * per-kernel totals and returns the number of distinct kernels (or a negative status);
+ * vkrs_profile_entry() reads one of them.  vkrs_set_profiling() clears the totals. */
+int vkrs_set_profiling(vkrs_handle handle, int enable);
+int vkrs_profile_collect(vkrs_handle handle);
+int vkrs_profile_entry(vkrs_handle handle, int index, const char **name, double *total_ms, uint64_t *launches);
 
 /* ---- introspection for tests / benches ---- */
 /* Number of kernel launches the handle has enqueued since creation. */

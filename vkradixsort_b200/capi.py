@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "vkrs_multi_histograms", "vkrs_multi_scatter", "vkrs_multi_pass",
     "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
     "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host",
-    "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant",
+    "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
+    "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry",
     "vkrs_launch_count", "vkrs_tile_size",
 ]
 
@@ -95,6 +96,11 @@ def load() -> ctypes.CDLL:
         "vkrs_num_variants": (i32, []),
         "vkrs_variant_name": (ctypes.c_char_p, [i32]),
         "vkrs_set_variant": (i32, [vp, i32]),
+        "vkrs_get_variant": (i32, [vp]),
+        "vkrs_set_profiling": (i32, [vp, i32]),
+        "vkrs_profile_collect": (i32, [vp]),
+        "vkrs_profile_entry": (i32, [vp, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(u64)]),
         "vkrs_launch_count": (u64, [vp]),
         "vkrs_tile_size": (u32, []),
     }
@@ -230,6 +236,26 @@ class Handle:
 
     def set_variant(self, variant: int):
         self._check(self._lib.vkrs_set_variant(self._h, variant))
+
+    @property
+    def variant(self) -> int:
+        return int(self._lib.vkrs_get_variant(self._h))
+
+    def set_profiling(self, enable: bool):
+        self._check(self._lib.vkrs_set_profiling(self._h, 1 if enable else 0))
+
+    def profile(self) -> dict:
+        """{kernel name: {"ms": total device ms, "launches": count}} since set_profiling(True)."""
+        k = self._lib.vkrs_profile_collect(self._h)
+        if k < 0:
+            self._check(k)
+        out = {}
+        for i in range(k):
+            name, ms, cnt = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_uint64()
+            self._check(self._lib.vkrs_profile_entry(self._h, i, ctypes.byref(name), ctypes.byref(ms),
+                                                     ctypes.byref(cnt)))
+            out[name.value.decode()] = {"ms": ms.value, "launches": cnt.value}
+        return out
 
     @property
     def launch_count(self) -> int:

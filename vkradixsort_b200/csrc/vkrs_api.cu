@@ -10,7 +10,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -68,6 +70,15 @@ struct vkrs_context {
     uint64_t staged_chunk_rows = 0;
     uint32_t *staged_bin_start = nullptr;
 
+    // opt-in per-kernel timing (vkrs_set_profiling): one event pair per launch
+    bool profiling = false;
+    struct ProfRecord {
+        const char *name;
+        cudaEvent_t start, stop;
+    };
+    std::vector<ProfRecord> prof_records;
+    std::vector<std::pair<std::string, std::pair<double, uint64_t>>> prof_summary; // name -> (ms, launches)
+
     // vkrs_multi_sort_host device buffers
     uint32_t *host_buf[2] = {nullptr, nullptr};
     uint64_t host_cap = 0;
@@ -85,6 +96,27 @@ int fail(vkrs_context *h, int code, const char *fmt, ...) {
     else g_create_error = buf;
     return code;
 }
+
+ // Brackets one kernel launch with an event pair when profiling is on; counts the launch.
+struct LaunchScope {
+    vkrs_context *h;
+    cudaStream_t stream;
+    cudaEvent_t stop = nullptr;
+    LaunchScope(vkrs_context *h_, const char *name, cudaStream_t s) : h(h_), stream(s) {
+        h->launches++;
+        if (!h->profiling) return;
+        cudaEvent_t start = nullptr;
+        if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
+            stop = nullptr;
+            return;
+        }
+        cudaEventRecord(start, stream);
+        h->prof_records.push_back({name, start, stop});
+    }
+    ~LaunchScope() {
+        if (stop) cudaEventRecord(stop, stream);
+    }
+};
 
 #define VKRS_CUDA(h, expr)                                                                                     \
     do {                                                                                                       \
@@ -154,11 +186,13 @@ int launch_pass_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
         configured_device = h->device;
     }
     const uint32_t tiles = (uint32_t) (((uint64_t) n + Sorter::TILE - 1) / Sorter::TILE);
-    kernel<<<tiles, THREADS, sizeof(typename Sorter::Smem), stream>>>(
-        in, out, vin, vout, n, shift, h->ctrl + pass_index * RADIX, h->status[pass_index & 1],
-        h->status[(pass_index + 1) & 1], h->ctrl + vkrs_context::CTRL_TICKETS + pass_index,
-        h->ctrl + vkrs_context::CTRL_ERROR);
-    h->launches++;
+    {
+        LaunchScope scope(h, HAS_VALUES ? "onesweep_pass_kernel<pairs>" : (sizeof(KeyT) == 8 ? "onesweep_pass_kernel<u64>" : "onesweep_pass_kernel"), stream);
+        kernel<<<tiles, THREADS, sizeof(typename Sorter::Smem), stream>>>(
+            in, out, vin, vout, n, shift, h->ctrl + pass_index * RADIX, h->status[pass_index & 1],
+            h->status[(pass_index + 1) & 1], h->ctrl + vkrs_context::CTRL_TICKETS + pass_index,
+            h->ctrl + vkrs_context::CTRL_ERROR);
+    }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
 }
@@ -202,9 +236,11 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
     if (per_cta == 0) per_cta = 2048;
     grid = ((uint64_t) n + per_cta - 1) / per_cta;
     if (grid == 0) grid = 1;
-    kernel<<<(unsigned) grid, HIST_THREADS, smem, stream>>>(keys, n, (uint32_t) per_cta, h->ctrl,
-                                                             h->ctrl + vkrs_context::CTRL_DONE);
-    h->launches++;
+    {
+        LaunchScope scope(h, "global_histogram_kernel", stream);
+        kernel<<<(unsigned) grid, HIST_THREADS, smem, stream>>>(keys, n, (uint32_t) per_cta, h->ctrl,
+                                                                 h->ctrl + vkrs_context::CTRL_DONE);
+    }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
 }
@@ -231,9 +267,11 @@ int check_multi_pc(vkrs_context *h, const vkrs_multi_push_constants *pc, bool ne
 
 int staged_histograms(vkrs_context *h, const uint32_t *in, uint32_t *hist, const vkrs_multi_push_constants *pc,
                       cudaStream_t stream) {
-    staged_histograms_kernel<<<pc->g_num_workgroups, STAGED_HIST_THREADS, 0, stream>>>(
-        in, hist, pc->g_num_elements, pc->g_shift, pc->g_num_blocks_per_workgroup);
-    h->launches++;
+    {
+        LaunchScope scope(h, "staged_histograms_kernel", stream);
+        staged_histograms_kernel<<<pc->g_num_workgroups, STAGED_HIST_THREADS, 0, stream>>>(
+            in, hist, pc->g_num_elements, pc->g_shift, pc->g_num_blocks_per_workgroup);
+    }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
 }
@@ -246,13 +284,22 @@ int staged_scatter(vkrs_context *h, const uint32_t *in, uint32_t *out, const uin
     if (r) return r;
     r = grow(h, h->staged_chunks, h->staged_chunk_rows, (uint64_t) chunks, RADIX * sizeof(uint32_t), false);
     if (r) return r;
-    staged_colsum_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks);
-    staged_chunkscan_kernel<<<1, 256, 0, stream>>>(h->staged_chunks, chunks, h->staged_bin_start);
-    staged_offsets_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks, h->staged_bin_start,
-                                                     h->staged_offsets);
-    h->launches += 3;
+    {
+        LaunchScope scope(h, "staged_colsum_kernel", stream);
+        staged_colsum_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks);
+    }
+    {
+        LaunchScope scope(h, "staged_chunkscan_kernel", stream);
+        staged_chunkscan_kernel<<<1, 256, 0, stream>>>(h->staged_chunks, chunks, h->staged_bin_start);
+    }
+    {
+        LaunchScope scope(h, "staged_offsets_kernel", stream);
+        staged_offsets_kernel<<<chunks, 256, 0, stream>>>(hist, W, h->staged_chunks, h->staged_bin_start,
+                                                         h->staged_offsets);
+    }
     VKRS_CUDA(h, cudaGetLastError());
 
+    LaunchScope scope(h, "staged_scatter_kernel", stream);
     if (vin) {
         using Sorter = TileSorter<uint32_t, true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT>;
         auto kernel = staged_scatter_kernel<true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT, 3>;
@@ -278,7 +325,6 @@ int staged_scatter(vkrs_context *h, const uint32_t *in, uint32_t *out, const uin
                                                                     pc->g_num_elements, pc->g_shift,
                                                                     pc->g_num_blocks_per_workgroup);
     }
-    h->launches++;
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
 }
@@ -372,6 +418,53 @@ int vkrs_destroy(vkrs_handle h) {
 const char *vkrs_last_error(vkrs_handle h) { return h ? h->error.c_str() : g_create_error.c_str(); }
 
 uint64_t vkrs_launch_count(vkrs_handle h) { return h ? h->launches : 0; }
+
+int vkrs_get_variant(vkrs_handle h) { return h ? h->variant : -1; }
+
+int vkrs_set_profiling(vkrs_handle h, int enable) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    VKRS_CUDA(h, cudaDeviceSynchronize());
+    for (auto &r : h->prof_records) {
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    h->prof_records.clear();
+    h->prof_summary.clear();
+    h->profiling = enable != 0;
+    return VKRS_OK;
+}
+
+// Folds the event pairs recorded so far into per-kernel totals; synchronises the device.
+int vkrs_profile_collect(vkrs_handle h) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    VKRS_CUDA(h, cudaDeviceSynchronize());
+    std::map<std::string, std::pair<double, uint64_t>> acc;
+    for (auto &s : h->prof_summary) acc[s.first] = s.second;
+    for (auto &r : h->prof_records) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.start, r.stop) == cudaSuccess) {
+            auto &a = acc[r.name];
+            a.first += ms;
+            a.second += 1;
+        }
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    h->prof_records.clear();
+    h->prof_summary.assign(acc.begin(), acc.end());
+    return (int) h->prof_summary.size();
+}
+
+int vkrs_profile_entry(vkrs_handle h, int index, const char **name, double *total_ms, uint64_t *launches) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (index < 0 || index >= (int) h->prof_summary.size()) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "profile index %d out of range", index);
+    if (name) *name = h->prof_summary[index].first.c_str();
+    if (total_ms) *total_ms = h->prof_summary[index].second.first;
+    if (launches) *launches = h->prof_summary[index].second.second;
+    return VKRS_OK;
+}
 
 int vkrs_set_variant(vkrs_handle h, int variant) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
@@ -538,8 +631,10 @@ int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_s
         if (r) return r;
         configured_device = h->device;
     }
-    kernel<<<1, SINGLE_THREADS, sizeof(Sorter::Smem), static_cast<cudaStream_t>(stream)>>>(buf0, buf1, n);
-    h->launches++;
+    {
+        LaunchScope scope(h, "single_sort_kernel", static_cast<cudaStream_t>(stream));
+        kernel<<<1, SINGLE_THREADS, sizeof(Sorter::Smem), static_cast<cudaStream_t>(stream)>>>(buf0, buf1, n);
+    }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
 }
