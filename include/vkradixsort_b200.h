@@ -155,6 +155,13 @@ int vkrs_set_profiling(vkrs_handle handle, int enable);
 int vkrs_profile_collect(vkrs_handle handle);
 int vkrs_profile_entry(vkrs_handle handle, int index, const char **name, double *total_ms, uint64_t *launches);
 
+/* Tuning aid: per-phase cycle counters of the pipelined kernel (control warp: [0] wait for tile
+ * counts, [1] claim + TMA issue, [2] look-back, [3] look-back polls, [4] tiles; worker warp 0:
+ * [8..15] wait for tile, rank, barrier, digit section, wait for prefix, write-out, barrier,
+ * scatter).  enable != 0 (re)starts counting, 0 stops; out (32 x uint64, may be NULL) receives the
+ * totals accumulated so far.  Synchronises the device. */
+int vkrs_debug_counters(vkrs_handle handle, int enable, uint64_t *out);
+
 /* ---- introspection for tests / benches ---- */
 /* Number of kernel launches the handle has enqueued since creation. */
 uint64_t vkrs_launch_count(vkrs_handle handle);

@@ -30,7 +30,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
     "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host",
     "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
-    "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry",
+    "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
 ]
 
@@ -97,6 +97,7 @@ def load() -> ctypes.CDLL:
         "vkrs_variant_name": (ctypes.c_char_p, [i32]),
         "vkrs_set_variant": (i32, [vp, i32]),
         "vkrs_get_variant": (i32, [vp]),
+        "vkrs_debug_counters": (i32, [vp, i32, ctypes.POINTER(u64)]),
         "vkrs_set_profiling": (i32, [vp, i32]),
         "vkrs_profile_collect": (i32, [vp]),
         "vkrs_profile_entry": (i32, [vp, i32, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_double),
@@ -240,6 +241,11 @@ class Handle:
     @property
     def variant(self) -> int:
         return int(self._lib.vkrs_get_variant(self._h))
+
+    def debug_counters(self, enable: bool) -> list:
+        out = (ctypes.c_uint64 * 32)()
+        self._check(self._lib.vkrs_debug_counters(self._h, 1 if enable else 0, out))
+        return list(out)
 
     def set_profiling(self, enable: bool):
         self._check(self._lib.vkrs_set_profiling(self._h, 1 if enable else 0))

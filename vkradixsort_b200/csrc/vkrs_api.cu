@@ -5,6 +5,7 @@
 // sm_100a kernels of vkrs_kernels.cuh or returns an error.
 #include "../../include/vkradixsort_b200.h"
 #include "vkrs_kernels.cuh"
+#include "vkrs_pipeline.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -25,11 +26,12 @@ struct PassConfig {
 };
 
 constexpr int NUM_VARIANTS = 8;
-// Keep in sync with launch_pass_u32() below.
+// Keep in sync with launch_pass_u32() below.  "pipe" = onesweep_pipelined_kernel (persistent,
+// TMA-fed, look-back on a control warp); "simple" = onesweep_pass_kernel (one tile per CTA).
 const PassConfig kVariants[NUM_VARIANTS] = {
-    {"512x16 ballot", 512, 16, 2}, {"512x16 match.any", 512, 16, 2}, {"256x16 ballot", 256, 16, 4},
-    {"256x16 match.any", 256, 16, 4}, {"384x20 ballot", 384, 20, 2}, {"512x12 ballot", 512, 12, 2},
-    {"256x24 ballot", 256, 24, 3},   {"1024x8 ballot", 1024, 8, 1},
+    {"pipe 384x16 r64/24", 384, 16, 2}, {"pipe 384x16 r64/24 ptx", 384, 16, 2}, {"pipe 256x24 r96/32", 256, 24, 2},
+    {"pipe 512x16 1cta", 512, 16, 1},   {"pipe 256x16 r56/24", 256, 16, 3}, {"simple 512x16 ptx", 512, 16, 2},
+    {"simple 256x24 ptx", 256, 24, 3}, {"simple 512x16 ballot", 512, 16, 2},
 };
 constexpr int DEFAULT_VARIANT = 0;
 
@@ -78,6 +80,9 @@ struct vkrs_context {
     };
     std::vector<ProfRecord> prof_records;
     std::vector<std::pair<std::string, std::pair<double, uint64_t>>> prof_summary; // name -> (ms, launches)
+
+    // phase timers of the pipelined kernel (tuning aid; NULL unless vkrs_debug_counters was enabled)
+    unsigned long long *debug_counters = nullptr;
 
     // vkrs_multi_sort_host device buffers
     uint32_t *host_buf[2] = {nullptr, nullptr};
@@ -197,17 +202,48 @@ int launch_pass_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
     return VKRS_OK;
 }
 
+// The pipelined kernel is persistent: the grid is the number of CTAs that are co-resident
+// (every CTA must be running for the chained scan to make progress), capped by the tile count.
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int MIN_BLOCKS, int REG_WORKER = 0, int REG_CTRL = 0,
+          int MATCH = MATCH_TABLE>
+int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                  uint32_t shift, int pass_index, cudaStream_t stream) {
+    using Smem = PipeSmem<KeyT, HAS_VALUES, WORKERS, KPT>;
+    auto kernel = onesweep_pipelined_kernel<KeyT, HAS_VALUES, WORKERS, KPT, MIN_BLOCKS, REG_WORKER, REG_CTRL, MATCH>;
+    static thread_local int configured_device = -1;
+    static thread_local int blocks_per_sm = 0;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, sizeof(Smem));
+        if (r) return r;
+        VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, WORKERS + CTRL_THREADS, sizeof(Smem)));
+        if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "pipelined kernel does not fit on an SM");
+        configured_device = h->device;
+    }
+    const uint64_t tiles = ((uint64_t) n + Smem::TILE - 1) / Smem::TILE;
+    uint64_t grid = (uint64_t) h->sm_count * blocks_per_sm;
+    if (grid > tiles) grid = tiles;
+    {
+        LaunchScope scope(h, HAS_VALUES ? "onesweep_pipelined_kernel<pairs>" : (sizeof(KeyT) == 8 ? "onesweep_pipelined_kernel<u64>" : "onesweep_pipelined_kernel"), stream);
+        kernel<<<(unsigned) grid, WORKERS + CTRL_THREADS, sizeof(Smem), stream>>>(
+            in, out, vin, vout, n, shift, h->ctrl + pass_index * RADIX, h->status[pass_index & 1],
+            h->status[(pass_index + 1) & 1], h->ctrl + vkrs_context::CTRL_TICKETS + pass_index,
+            h->ctrl + vkrs_context::CTRL_ERROR, h->debug_counters);
+    }
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
 int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t shift, int pass_index,
                     cudaStream_t stream) {
     switch (h->variant) {
-        case 0: return launch_pass_t<uint32_t, false, 512, 16, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 1: return launch_pass_t<uint32_t, false, 512, 16, MATCH_HW, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 2: return launch_pass_t<uint32_t, false, 256, 16, MATCH_BALLOT, 4>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 3: return launch_pass_t<uint32_t, false, 256, 16, MATCH_HW, 4>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 4: return launch_pass_t<uint32_t, false, 384, 20, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 5: return launch_pass_t<uint32_t, false, 512, 12, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 6: return launch_pass_t<uint32_t, false, 256, 24, MATCH_BALLOT, 3>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 7: return launch_pass_t<uint32_t, false, 1024, 8, MATCH_BALLOT, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 0: return launch_pipe_t<uint32_t, false, 384, 16, 2, 64, 24>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 1: return launch_pipe_t<uint32_t, false, 384, 16, 2, 64, 24, MATCH_PTX>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 2: return launch_pipe_t<uint32_t, false, 256, 24, 2, 96, 32>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 3: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 4: return launch_pipe_t<uint32_t, false, 256, 16, 3, 56, 24>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 5: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 6: return launch_pass_t<uint32_t, false, 256, 24, MATCH_PTX, 3>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
         default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", h->variant);
     }
 }
@@ -301,8 +337,8 @@ int staged_scatter(vkrs_context *h, const uint32_t *in, uint32_t *out, const uin
 
     LaunchScope scope(h, "staged_scatter_kernel", stream);
     if (vin) {
-        using Sorter = TileSorter<uint32_t, true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT>;
-        auto kernel = staged_scatter_kernel<true, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT, 3>;
+        using Sorter = TileSorter<uint32_t, true, STAGED_THREADS, STAGED_KPT, MATCH_PTX>;
+        auto kernel = staged_scatter_kernel<true, STAGED_THREADS, STAGED_KPT, MATCH_PTX, 3>;
         static thread_local int configured_device = -1;
         if (configured_device != h->device) {
             r = set_smem(h, kernel, sizeof(Sorter::Smem));
@@ -313,8 +349,8 @@ int staged_scatter(vkrs_context *h, const uint32_t *in, uint32_t *out, const uin
                                                                     pc->g_num_elements, pc->g_shift,
                                                                     pc->g_num_blocks_per_workgroup);
     } else {
-        using Sorter = TileSorter<uint32_t, false, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT>;
-        auto kernel = staged_scatter_kernel<false, STAGED_THREADS, STAGED_KPT, MATCH_BALLOT, 4>;
+        using Sorter = TileSorter<uint32_t, false, STAGED_THREADS, STAGED_KPT, MATCH_PTX>;
+        auto kernel = staged_scatter_kernel<false, STAGED_THREADS, STAGED_KPT, MATCH_PTX, 4>;
         static thread_local int configured_device = -1;
         if (configured_device != h->device) {
             r = set_smem(h, kernel, sizeof(Sorter::Smem));
@@ -409,6 +445,7 @@ int vkrs_destroy(vkrs_handle h) {
     cudaFree(h->staged_offsets);
     cudaFree(h->staged_chunks);
     cudaFree(h->staged_bin_start);
+    cudaFree(h->debug_counters);
     cudaFree(h->host_buf[0]);
     cudaFree(h->host_buf[1]);
     delete h;
@@ -420,6 +457,26 @@ const char *vkrs_last_error(vkrs_handle h) { return h ? h->error.c_str() : g_cre
 uint64_t vkrs_launch_count(vkrs_handle h) { return h ? h->launches : 0; }
 
 int vkrs_get_variant(vkrs_handle h) { return h ? h->variant : -1; }
+
+// Tuning aid: phase timers of the pipelined kernel.  enable != 0 allocates/zeroes 32 device
+// counters that the kernels accumulate into; out (may be NULL) receives the current values.
+int vkrs_debug_counters(vkrs_handle h, int enable, uint64_t *out) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    VKRS_CUDA(h, cudaDeviceSynchronize());
+    if (out) {
+        if (h->debug_counters) VKRS_CUDA(h, cudaMemcpy(out, h->debug_counters, 32 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        else memset(out, 0, 32 * sizeof(uint64_t));
+    }
+    if (enable) {
+        if (!h->debug_counters) VKRS_CUDA(h, cudaMalloc(&h->debug_counters, 32 * sizeof(uint64_t)));
+        VKRS_CUDA(h, cudaMemset(h->debug_counters, 0, 32 * sizeof(uint64_t)));
+    } else if (h->debug_counters) {
+        cudaFree(h->debug_counters);
+        h->debug_counters = nullptr;
+    }
+    return VKRS_OK;
+}
 
 int vkrs_set_profiling(vkrs_handle h, int enable) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
@@ -584,7 +641,7 @@ int vkrs_multi_sort_pairs(vkrs_handle h, uint32_t *keys0, uint32_t *keys1, uint3
     for (int p = 0; p < 4; ++p) {
         uint32_t *in = (p & 1) ? keys1 : keys0, *out = (p & 1) ? keys0 : keys1;
         uint32_t *vin = (p & 1) ? values1 : values0, *vout = (p & 1) ? values0 : values1;
-        r = launch_pass_t<uint32_t, true, PAIR_THREADS, PAIR_KPT, MATCH_BALLOT, 2>(h, in, out, vin, vout, n, 8 * p, p, s);
+        r = launch_pass_t<uint32_t, true, PAIR_THREADS, PAIR_KPT, MATCH_PTX, 2>(h, in, out, vin, vout, n, 8 * p, p, s);
         if (r) return r;
     }
     return VKRS_OK;
@@ -608,7 +665,7 @@ int vkrs_multi_sort_u64(vkrs_handle h, uint64_t *buf0, uint64_t *buf1, uint32_t 
     if (r) return r;
     for (int p = 0; p < 8; ++p) { // NUM_ITERATIONS = 8, MultiRadixSort.cpp:54
         K *in = reinterpret_cast<K *>((p & 1) ? buf1 : buf0), *out = reinterpret_cast<K *>((p & 1) ? buf0 : buf1);
-        r = launch_pass_t<K, false, U64_THREADS, U64_KPT, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, 8 * p, p, s);
+        r = launch_pass_t<K, false, U64_THREADS, U64_KPT, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, 8 * p, p, s);
         if (r) return r;
     }
     return VKRS_OK;
@@ -623,8 +680,8 @@ int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_s
     if (n >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "g_num_elements=%u: at most 2^30-1 keys per call", n);
     if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
-    using Sorter = TileSorter<uint32_t, false, SINGLE_THREADS, SINGLE_KPT, MATCH_BALLOT>;
-    auto kernel = single_sort_kernel<SINGLE_THREADS, SINGLE_KPT, MATCH_BALLOT>;
+    using Sorter = TileSorter<uint32_t, false, SINGLE_THREADS, SINGLE_KPT, MATCH_PTX>;
+    auto kernel = single_sort_kernel<SINGLE_THREADS, SINGLE_KPT, MATCH_PTX>;
     static thread_local int configured_device = -1;
     if (configured_device != h->device) {
         int r = set_smem(h, kernel, sizeof(Sorter::Smem));

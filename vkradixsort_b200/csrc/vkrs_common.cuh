@@ -14,7 +14,8 @@ constexpr uint32_t STATUS_FLAG_AGGREGATE = 1u << 30; // this tile's own digit co
 constexpr uint32_t STATUS_FLAG_INCLUSIVE = 2u << 30; // count of this tile and all tiles before it
 constexpr uint32_t STATUS_FLAG_MASK = 3u << 30;
 constexpr uint32_t STATUS_VALUE_MASK = ~STATUS_FLAG_MASK;
-constexpr uint32_t LOOKBACK_SPIN_LIMIT = 1u << 24; // polls before a tile gives up and raises the error flag
+constexpr uint32_t LOOKBACK_SPIN_LIMIT = 1u << 22;
+constexpr int LOOKBACK_WINDOW = 8;                  // earlier tiles polled together by one digit thread // polls before a tile gives up and raises the error flag
 
 enum DeviceError : uint32_t { DEVERR_NONE = 0, DEVERR_LOOKBACK_TIMEOUT = 1 };
 
@@ -45,10 +46,106 @@ __device__ __forceinline__ uint32_t digit_of(KeyT key, uint32_t shift) {
     return static_cast<uint32_t>(key >> shift) & (RADIX - 1);
 }
 
+__device__ __forceinline__ uint32_t lanemask_gt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_gt;" : "=r"(m));
+    return m;
+}
+
 // Peer mask of the lanes holding the same 8-bit digit.
-//   MATCH_BALLOT: 8 ballots + LOP3s (no shared memory, no special unit)
-//   MATCH_HW    : the match.any instruction
-enum MatchMode { MATCH_BALLOT = 0, MATCH_HW = 1 };
+//   MATCH_BALLOT: 8 ballots + LOP3s as the compiler schedules them
+//   MATCH_HW    : the match.any instruction (measured slower than ballots on B200)
+//   MATCH_PTX   : 8 ballots, hand-scheduled: per bit one predicate-producing AND on the key
+//                 itself, one vote, one predicated fold (3 ALU-pipe + 1 vote instruction per bit;
+//                 the compiler's version needs 5 + 1) -- see match_key_ptx()
+//   MATCH_TABLE : 8 ballots, then two 16-entry nibble tables spread over the lanes and two
+//                 shuffles -- see match_key_table()
+enum MatchMode { MATCH_BALLOT = 0, MATCH_HW = 1, MATCH_PTX = 2, MATCH_TABLE = 3 };
+
+// The eight single-bit masks of the current digit, 1 << (shift + b).  Uniform per kernel.
+struct DigitBitMasks {
+    uint32_t m[RADIX_BITS];
+    __device__ __forceinline__ explicit DigitBitMasks(uint32_t shift) {
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; ++b) m[b] = 1u << (shift + b);
+    }
+};
+
+#define VKRS_MATCH_BIT(N)                                            \
+    "and.b32 t, %1, %" #N ";\n\t"                                    \
+    "setp.ne.u32 p, t, 0;\n\t"                                       \
+    "vote.sync.ballot.b32 v, p, 0xffffffff;\n\t"                     \
+    "@p and.b32 m, m, v;\n\t"                                        \
+    "@!p lop3.b32 m, m, v, 0, 0x30;\n\t" /* m & ~v */
+
+// Lanes of the warp whose key has the same digit (the 8 bits selected by `bm`).  All 32 lanes
+// must call it (vote.sync over the full warp).  Works on 32-bit key words; 64-bit keys pass the
+// word that holds the digit.
+__device__ __forceinline__ uint32_t match_key_ptx(uint32_t key_word, const DigitBitMasks &bm) {
+    uint32_t peers;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t, v, m;\n\t"
+        "mov.b32 m, 0xffffffff;\n\t"
+        VKRS_MATCH_BIT(2) VKRS_MATCH_BIT(3) VKRS_MATCH_BIT(4) VKRS_MATCH_BIT(5)
+        VKRS_MATCH_BIT(6) VKRS_MATCH_BIT(7) VKRS_MATCH_BIT(8) VKRS_MATCH_BIT(9)
+        "mov.b32 %0, m;\n\t"
+        "}"
+        : "=r"(peers)
+        : "r"(key_word), "r"(bm.m[0]), "r"(bm.m[1]), "r"(bm.m[2]), "r"(bm.m[3]), "r"(bm.m[4]), "r"(bm.m[5]),
+          "r"(bm.m[6]), "r"(bm.m[7]));
+    return peers;
+}
+#undef VKRS_MATCH_BIT
+
+// Ballot of "key has this bit set": one predicate-producing AND + one vote (the compiler's own
+// rendering of the same C expression is shift + mask + compare + vote).
+__device__ __forceinline__ uint32_t ballot_bit(uint32_t key_word, uint32_t bit_mask) {
+    uint32_t v;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 t;\n\t"
+        "and.b32 t, %1, %2;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+        "}"
+        : "=r"(v)
+        : "r"(key_word), "r"(bit_mask));
+    return v;
+}
+
+// Per-lane constants of match_key_table(): c[b] = all-ones iff bit b of (lane & 15) is CLEAR.
+struct LaneNibbleConsts {
+    uint32_t c[4];
+    __device__ __forceinline__ explicit LaneNibbleConsts(int lane) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[b] = ((lane >> b) & 1) ? 0u : 0xffffffffu;
+    }
+};
+
+// Peer mask through nibble tables.  The eight ballots B_b (lanes whose key has digit bit b set)
+// are warp-uniform.  Lane i turns them into two table entries with 8 logic ops whose selectors
+// are lane constants, not data:  lo = lanes whose low digit nibble == (i & 15), hi = lanes whose
+// high nibble == (i & 15).  A lane then fetches the two entries that belong to ITS digit with
+// two shuffles: peers = lo[d & 15] & hi[d >> 4].  ~19 ALU-pipe instructions + 8 votes +
+// 2 shuffles per key, against ~32 + 8 for folding the ballots with per-lane selects.
+__device__ __forceinline__ uint32_t match_key_table(uint32_t key_word, uint32_t digit, const DigitBitMasks &bm,
+                                                    const LaneNibbleConsts &lc) {
+    uint32_t B[RADIX_BITS];
+#pragma unroll
+    for (int b = 0; b < RADIX_BITS; ++b) B[b] = ballot_bit(key_word, bm.m[b]);
+    const uint32_t lo = (B[0] ^ lc.c[0]) & (B[1] ^ lc.c[1]) & (B[2] ^ lc.c[2]) & (B[3] ^ lc.c[3]);
+    const uint32_t hi = (B[4] ^ lc.c[0]) & (B[5] ^ lc.c[1]) & (B[6] ^ lc.c[2]) & (B[7] ^ lc.c[3]);
+    return __shfl_sync(0xffffffffu, lo, (int) (digit & 15u)) & __shfl_sync(0xffffffffu, hi, (int) (digit >> 4));
+}
+
+// Byte extraction of the current digit (shift is a multiple of 8): one PRMT instead of shift + mask.
+__device__ __forceinline__ uint32_t digit_selector(uint32_t shift) { return 0x4440u + ((shift & 31u) >> 3); }
+__device__ __forceinline__ uint32_t digit_prmt(uint32_t key_word, uint32_t selector) {
+    return __byte_perm(key_word, 0u, selector);
+}
 
 template <int MODE>
 __device__ __forceinline__ uint32_t match_digit(uint32_t digit) {

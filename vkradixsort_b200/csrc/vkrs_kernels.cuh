@@ -121,6 +121,65 @@ global_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t keys
 //   status_clear[tile][digit]  the array the next pass will use; zeroed here so no memset
 //                              sits between passes.
 // =====================================================================================
+struct ChainedScanBase {
+    uint32_t *status, *status_clear;
+    const uint32_t *bin_start;
+    uint32_t *error_flag;
+    uint32_t tile;
+
+    __device__ __forceinline__ void publish(uint32_t d, uint32_t count) const {
+        st_relaxed_gpu(status + (size_t) tile * RADIX + d,
+                       (tile == 0 ? STATUS_FLAG_INCLUSIVE : STATUS_FLAG_AGGREGATE) | count);
+        if (status_clear) status_clear[(size_t) tile * RADIX + d] = 0;
+    }
+    // Windowed look-back: LOOKBACK_WINDOW earlier tiles are polled together (independent loads in
+    // flight), then consumed nearest-first up to the first INCLUSIVE word.  On B200 a tile retires
+    // every few tens of ns while one L2 round trip is a few hundred, so ~10 predecessors have only
+    // their AGGREGATE out when a tile looks back: walking them one load at a time is what stalls.
+    template <int WINDOW = LOOKBACK_WINDOW, int BACKOFF_NS = 0>
+    __device__ __forceinline__ uint32_t resolve(uint32_t d, uint32_t count) const {
+        uint32_t excl = 0;
+        if (tile != 0) {
+            uint32_t *my = status + (size_t) tile * RADIX + d;
+            uint32_t back = 1; // distance of the nearest tile not yet consumed
+            uint32_t spins = 0;
+            bool done = false;
+            while (!done) {
+                uint32_t w[WINDOW];
+#pragma unroll
+                for (int i = 0; i < WINDOW; ++i)
+                    w[i] = (back + i <= tile) ? ld_relaxed_gpu(my - (size_t) (back + i) * RADIX) : 0u;
+#pragma unroll
+                for (int i = 0; i < WINDOW; ++i) {
+                    if (done || (w[i] & STATUS_FLAG_MASK) == 0) break; // unpublished: poll again from here
+                    excl += w[i] & STATUS_VALUE_MASK;
+                    back++;
+                    if (w[i] & STATUS_FLAG_INCLUSIVE) done = true; // tile 0 always publishes INCLUSIVE
+                }
+                if (++spins > LOOKBACK_SPIN_LIMIT) {
+                    atomicExch(error_flag, (uint32_t) DEVERR_LOOKBACK_TIMEOUT);
+                    break;
+                }
+                if (BACKOFF_NS > 0 && !done && (w[0] & STATUS_FLAG_MASK) == 0) __nanosleep(BACKOFF_NS); // nothing new: leave the issue slots to the workers
+            }
+            st_relaxed_gpu(my, STATUS_FLAG_INCLUSIVE | ((excl + count) & STATUS_VALUE_MASK));
+        }
+        return bin_start[d] + excl;
+    }
+};
+
+// Running per-digit offsets in shared memory: the staged and single-workgroup paths, where one
+// CTA walks its slab tile by tile (global_offsets[] of multi_radixsort.comp:75-76,120-122).
+struct RunningOffsetsBase {
+    uint32_t *global_offsets;
+    __device__ __forceinline__ void publish(uint32_t, uint32_t) const {}
+    __device__ __forceinline__ uint32_t resolve(uint32_t d, uint32_t count) const {
+        const uint32_t g = global_offsets[d];
+        global_offsets[d] = g + count;
+        return g;
+    }
+};
+
 template <typename KeyT, bool HAS_VALUES, int THREADS, int KPT, int MATCH, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
@@ -139,36 +198,9 @@ onesweep_pass_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_o
     if (tile_base >= n) return; // cannot happen with grid == number of tiles; kept as a guard
     const uint32_t valid = (n - tile_base < TILE) ? (uint32_t) (n - tile_base) : TILE;
 
-    auto base_fn = [&](uint32_t d, uint32_t count) -> uint32_t {
-        uint32_t *my = status + (size_t) tile * RADIX + d;
-        uint32_t excl = 0;
-        if (tile == 0) {
-            st_relaxed_gpu(my, STATUS_FLAG_INCLUSIVE | count);
-        } else {
-            st_relaxed_gpu(my, STATUS_FLAG_AGGREGATE | count);
-            const uint32_t *p = my - RADIX;
-            uint32_t spins = 0;
-            while (true) {
-                const uint32_t w = ld_relaxed_gpu(p);
-                if ((w & STATUS_FLAG_MASK) == 0) {
-                    if (++spins > LOOKBACK_SPIN_LIMIT) {
-                        atomicExch(error_flag, (uint32_t) DEVERR_LOOKBACK_TIMEOUT);
-                        break;
-                    }
-                    continue;
-                }
-                excl += w & STATUS_VALUE_MASK;
-                if (w & STATUS_FLAG_INCLUSIVE) break;
-                p -= RADIX; // tile 0 always publishes INCLUSIVE, so this never runs off the front
-            }
-            st_relaxed_gpu(my, STATUS_FLAG_INCLUSIVE | ((excl + count) & STATUS_VALUE_MASK));
-        }
-        if (status_clear) status_clear[(size_t) tile * RADIX + d] = 0;
-        return bin_start[d] + excl;
-    };
-
+    ChainedScanBase base{status, status_clear, bin_start, error_flag, tile};
     Sorter::run(s, keys_in + tile_base, keys_out, HAS_VALUES ? vals_in + tile_base : nullptr, vals_out, valid, shift,
-                base_fn);
+                base);
 }
 
 // =====================================================================================
@@ -272,11 +304,7 @@ staged_scatter_kernel(const uint32_t *__restrict__ elements_in, uint32_t *__rest
     const uint64_t slab = (uint64_t) nb * 256u;
     const uint64_t lo = (uint64_t) blockIdx.x * slab;
     const uint64_t hi = (lo + slab < n) ? lo + slab : n;
-    auto base_fn = [&](uint32_t d, uint32_t count) -> uint32_t {
-        const uint32_t g = global_offsets[d];
-        global_offsets[d] = g + count;
-        return g;
-    };
+    RunningOffsetsBase base_fn{global_offsets};
     __syncthreads();
     for (uint64_t t0 = lo; t0 < hi; t0 += TILE) {
         const uint32_t valid = (hi - t0 < TILE) ? (uint32_t) (hi - t0) : TILE;
@@ -315,11 +343,7 @@ single_sort_kernel(uint32_t *buf0, uint32_t *buf1, uint32_t n) {
         const uint32_t ex = block_exclusive_scan_256(tid < RADIX ? histogram[tid] : 0u, s_scan, nullptr); // :65-84
         if (tid < RADIX) global_offsets[tid] = ex;
         __syncthreads();
-        auto base_fn = [&](uint32_t d, uint32_t count) -> uint32_t {
-            const uint32_t g = global_offsets[d];
-            global_offsets[d] = g + count;
-            return g;
-        };
+        RunningOffsetsBase base_fn{global_offsets};
         for (uint32_t t0 = 0; t0 < n; t0 += TILE) { // :91
             const uint32_t valid = (n - t0 < TILE) ? (n - t0) : TILE;
             Sorter::run(s, src + t0, dst, nullptr, nullptr, valid, shift, base_fn);

@@ -42,11 +42,16 @@ struct TileSorter {
     using Smem = TileSmem<KeyT, THREADS, KPT>;
 
     // keys_in/vals_in point at the first key of the tile; `valid` (<= TILE) keys exist.
-    // base_fn(digit, count) is called by threads 0..255 (digit == threadIdx.x) between two
-    // block barriers and returns the global index where this tile's run of `digit` starts.
-    template <class BaseFn>
+    // `base` is called by threads 0..255 (digit == threadIdx.x):
+    //   base.publish(digit, count)  as soon as the tile's digit counts are known (the fused path
+    //                               posts its AGGREGATE status word here, so later tiles can move on);
+    //   base.resolve(digit, count)  as late as possible -- after this thread's keys are already in
+    //                               their tile slots -- returns the global index where this tile's
+    //                               run of `digit` starts (the fused path's look-back; by now the
+    //                               earlier tiles have had time to publish, so the wait is short).
+    template <class Base>
     static __device__ __forceinline__ void run(Smem &s, const KeyT *keys_in, KeyT *keys_out, const uint32_t *vals_in,
-                                               uint32_t *vals_out, uint32_t valid, uint32_t shift, BaseFn base_fn) {
+                                               uint32_t *vals_out, uint32_t valid, uint32_t shift, Base base) {
         const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
         const bool full = valid == TILE;
 
@@ -78,25 +83,30 @@ struct TileSorter {
         __syncwarp();
 
         // ---- rank inside the warp ----
+        // Per round every lane reads the warp's running count of its digit, adds the number of
+        // lower lanes holding the same digit, and the highest lane of each group stores the
+        // bumped count back -- the role of `prefix == count - 1` in multi_radixsort.comp:120-122.
         // ranks are < TILE <= 65536: two per register
         static_assert(KPT % 2 == 0, "ranks are packed in pairs");
         uint32_t rank2[KPT / 2];
-        const uint32_t lt_mask = lanemask_lt();
+        const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
+        const DigitBitMasks bm(sizeof(KeyT) == 8 ? (shift & 31u) : shift);
+        uint32_t *my_cnt = s.warp_cnt[warp];
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             const uint32_t d = digit_of(key[i], shift);
-            const uint32_t peers = match_digit<MATCH>(d);
-            const uint32_t lower = peers & lt_mask;
-            uint32_t old = 0;
-            if (lower == 0) { // lowest lane of the group
-                old = s.warp_cnt[warp][d];
-                s.warp_cnt[warp][d] = old + __popc(peers);
+            uint32_t peers;
+            if (MATCH == MATCH_PTX) {
+                const uint32_t word = sizeof(KeyT) == 8 ? (uint32_t) ((uint64_t) key[i] >> (shift & 32u)) : (uint32_t) key[i];
+                peers = match_key_ptx(word, bm);
+            } else {
+                peers = match_digit<MATCH>(d);
             }
-            old = __shfl_sync(0xffffffffu, old, __ffs(peers) - 1);
-            const uint32_t r = old + __popc(lower);
+            const uint32_t r = my_cnt[d] + __popc(peers & lt_mask);
+            if ((peers & gt_mask) == 0) my_cnt[d] = r + 1; // highest lane of the group
             if (i & 1) rank2[i / 2] |= r << 16;
             else rank2[i / 2] = r;
-            __syncwarp(); // counter update visible to the next round's leaders
+            __syncwarp(); // counter update visible to the next round
         }
         __syncthreads();
 
@@ -108,8 +118,7 @@ struct TileSorter {
         }
         uint32_t counted = total; // what the rest of the grid must see: real keys only
         if (!full && tid == RADIX - 1) counted -= (TILE - valid);
-        uint32_t gbase = 0;
-        if (tid < RADIX) gbase = base_fn((uint32_t) tid, counted);
+        if (tid < RADIX) base.publish((uint32_t) tid, counted);
         const uint32_t local_excl = block_exclusive_scan_256(tid < RADIX ? total : 0u, s.scan_scratch, nullptr);
         if (tid < RADIX) {
             uint32_t running = local_excl;
@@ -119,7 +128,6 @@ struct TileSorter {
                 s.warp_cnt[w][tid] = running;
                 running += c;
             }
-            s.bin_dst[tid] = gbase - local_excl;
         }
         __syncthreads();
 
@@ -134,6 +142,7 @@ struct TileSorter {
             }
             s.tile[r] = key[i];
         }
+        if (tid < RADIX) s.bin_dst[tid] = base.resolve((uint32_t) tid, counted) - local_excl;
         __syncthreads();
 
         // ---- write out in tile order ----
