@@ -6,6 +6,7 @@
 #include "../../include/vkradixsort_b200.h"
 #include "vkrs_kernels.cuh"
 #include "vkrs_pipeline.cuh"
+#include "vkrs_segmented.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -26,18 +27,20 @@ struct PassConfig {
 };
 
 constexpr int NUM_VARIANTS = 8;
-// Keep in sync with launch_pass_u32() below.  "pipe" = onesweep_pipelined_kernel (persistent,
-// TMA-fed, look-back on a control warp); "simple" = onesweep_pass_kernel (one tile per CTA).
+// Keep in sync with launch_pass_u32() below.
+//   "seg"    = segment_histogram_kernel + segmented_scatter_kernel (count first, no inter-CTA chain)
+//   "pipe"   = onesweep_pipelined_kernel (single sweep, persistent, look-back on a control group)
+//   "simple" = onesweep_pass_kernel (single sweep, one tile per CTA)
 const PassConfig kVariants[NUM_VARIANTS] = {
-    {"pipe 384x16 r64/24", 384, 16, 2}, {"pipe 384x16 r64/24 ptx", 384, 16, 2}, {"pipe 256x24 r96/32", 256, 24, 2},
-    {"pipe 512x16 1cta", 512, 16, 1},   {"pipe 256x16 r56/24", 256, 16, 3}, {"simple 512x16 ptx", 512, 16, 2},
-    {"simple 256x24 ptx", 256, 24, 3}, {"simple 512x16 ballot", 512, 16, 2},
+    {"seg 2x384x16", 384, 16, 1},  {"seg 2x480x16", 480, 16, 1},  {"seg 2x384x20", 384, 20, 1},
+    {"seg 3x256x20", 256, 20, 1},  {"seg 3x320x16", 320, 16, 1},  {"seg 1x512x12 2cta", 512, 12, 2},
+    {"pipe 512x16 1cta", 512, 16, 1}, {"simple 512x16 ptx", 512, 16, 2},
 };
 constexpr int DEFAULT_VARIANT = 0;
 
 // default configurations of the other paths
-constexpr int PAIR_THREADS = 512, PAIR_KPT = 12;
-constexpr int U64_THREADS = 512, U64_KPT = 8;
+constexpr int PAIR_WORKERS = 256, PAIR_KPT = 16; // segmented path, two worker groups per CTA
+constexpr int U64_WORKERS = 256, U64_KPT = 16;
 constexpr int STAGED_THREADS = 256, STAGED_KPT = 16;
 constexpr int SINGLE_THREADS = 1024, SINGLE_KPT = 8;
 constexpr uint32_t AUTO_SINGLE_MAX = 4096; // vkrs_sort_auto: single path up to here (tuned on B200)
@@ -64,6 +67,10 @@ struct vkrs_context {
     // chained-scan tile status, two arrays used alternately by consecutive passes
     uint32_t *status[2] = {nullptr, nullptr};
     uint64_t status_rows = 0;
+
+    // segmented path: hist[segments][256]
+    uint32_t *seg_hist = nullptr;
+    uint64_t seg_hist_rows = 0;
 
     // staged path: offsets[W][256], chunk sums, bin starts
     uint32_t *staged_offsets = nullptr;
@@ -205,17 +212,17 @@ int launch_pass_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
 // The pipelined kernel is persistent: the grid is the number of CTAs that are co-resident
 // (every CTA must be running for the chained scan to make progress), capped by the tile count.
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int MIN_BLOCKS, int REG_WORKER = 0, int REG_CTRL = 0,
-          int MATCH = MATCH_TABLE>
+          int MATCH = MATCH_TABLE, int GROUPS = 1>
 int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
                   uint32_t shift, int pass_index, cudaStream_t stream) {
-    using Smem = PipeSmem<KeyT, HAS_VALUES, WORKERS, KPT>;
-    auto kernel = onesweep_pipelined_kernel<KeyT, HAS_VALUES, WORKERS, KPT, MIN_BLOCKS, REG_WORKER, REG_CTRL, MATCH>;
+    using Smem = PipeSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
+    auto kernel = onesweep_pipelined_kernel<KeyT, HAS_VALUES, WORKERS, KPT, MIN_BLOCKS, REG_WORKER, REG_CTRL, MATCH, GROUPS>;
     static thread_local int configured_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (configured_device != h->device) {
         int r = set_smem(h, kernel, sizeof(Smem));
         if (r) return r;
-        VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, WORKERS + CTRL_THREADS, sizeof(Smem)));
+        VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, GROUPS * WORKERS + CTRL_THREADS, sizeof(Smem)));
         if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "pipelined kernel does not fit on an SM");
         configured_device = h->device;
     }
@@ -224,7 +231,7 @@ int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
     if (grid > tiles) grid = tiles;
     {
         LaunchScope scope(h, HAS_VALUES ? "onesweep_pipelined_kernel<pairs>" : (sizeof(KeyT) == 8 ? "onesweep_pipelined_kernel<u64>" : "onesweep_pipelined_kernel"), stream);
-        kernel<<<(unsigned) grid, WORKERS + CTRL_THREADS, sizeof(Smem), stream>>>(
+        kernel<<<(unsigned) grid, GROUPS * WORKERS + CTRL_THREADS, sizeof(Smem), stream>>>(
             in, out, vin, vout, n, shift, h->ctrl + pass_index * RADIX, h->status[pass_index & 1],
             h->status[(pass_index + 1) & 1], h->ctrl + vkrs_context::CTRL_TICKETS + pass_index,
             h->ctrl + vkrs_context::CTRL_ERROR, h->debug_counters);
@@ -233,20 +240,59 @@ int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
     return VKRS_OK;
 }
 
+// One digit pass of the segmented path: count (one CTA per segment), then the persistent scatter.
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS>
+int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
+                 uint32_t shift, cudaStream_t stream) {
+    using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
+    constexpr uint32_t TILE = Smem::Group::TILE;
+    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS>;
+    static thread_local int configured_device = -1;
+    static thread_local int blocks_per_sm = 0;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, sizeof(Smem));
+        if (r) return r;
+        VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, GROUPS * WORKERS + 32, sizeof(Smem)));
+        if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "segmented scatter kernel does not fit on an SM");
+        configured_device = h->device;
+    }
+    const uint32_t tiles = (uint32_t) (((uint64_t) n + TILE - 1) / TILE);
+    uint32_t ctas = (uint32_t) (h->sm_count * blocks_per_sm);
+    const uint32_t need = (tiles + GROUPS - 1) / GROUPS;
+    if (ctas > need) ctas = need;
+    if (ctas == 0) ctas = 1;
+    const uint32_t segments = ctas * GROUPS;
+    int r = grow(h, h->seg_hist, h->seg_hist_rows, (uint64_t) segments, RADIX * sizeof(uint32_t), false);
+    if (r) return r;
+    {
+        LaunchScope scope(h, "segment_histogram_kernel", stream);
+        segment_histogram_kernel<KeyT><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, TILE, tiles, h->seg_hist);
+    }
+    {
+        LaunchScope scope(h, HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
+        kernel<<<ctas, GROUPS * WORKERS + 32, sizeof(Smem), stream>>>(in, out, vin, vout, n, shift, h->seg_hist, tiles,
+                                                                      h->debug_counters);
+    }
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
 int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t shift, int pass_index,
                     cudaStream_t stream) {
     switch (h->variant) {
-        case 0: return launch_pipe_t<uint32_t, false, 384, 16, 2, 64, 24>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 1: return launch_pipe_t<uint32_t, false, 384, 16, 2, 64, 24, MATCH_PTX>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 2: return launch_pipe_t<uint32_t, false, 256, 24, 2, 96, 32>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 3: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 4: return launch_pipe_t<uint32_t, false, 256, 16, 3, 56, 24>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 5: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 6: return launch_pass_t<uint32_t, false, 256, 24, MATCH_PTX, 3>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 0: return launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 1: return launch_seg_t<uint32_t, false, 480, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 2: return launch_seg_t<uint32_t, false, 384, 20, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 3: return launch_seg_t<uint32_t, false, 256, 20, 3, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 4: return launch_seg_t<uint32_t, false, 320, 16, 3, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 5: return launch_seg_t<uint32_t, false, 512, 12, 1, 2>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 6: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
         default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", h->variant);
     }
 }
+
+bool variant_is_segmented(int v) { return strncmp(kVariants[v].name, "seg", 3) == 0; }
 
 uint32_t variant_tile(int v) { return (uint32_t) (kVariants[v].threads * kVariants[v].kpt); }
 
@@ -442,6 +488,7 @@ int vkrs_destroy(vkrs_handle h) {
     cudaFree(h->ctrl);
     cudaFree(h->status[0]);
     cudaFree(h->status[1]);
+    cudaFree(h->seg_hist);
     cudaFree(h->staged_offsets);
     cudaFree(h->staged_chunks);
     cudaFree(h->staged_bin_start);
@@ -610,11 +657,13 @@ int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *his
     if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const uint32_t tile = variant_tile(h->variant);
-    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
-    if (r) return r;
-    r = launch_global_histogram<uint32_t, 4>(h, buf0, n, s);
-    if (r) return r;
+    if (!variant_is_segmented(h->variant)) { // the single-sweep variants need the global digit starts
+        const uint32_t tile = variant_tile(h->variant);
+        r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
+        if (r) return r;
+        r = launch_global_histogram<uint32_t, 4>(h, buf0, n, s);
+        if (r) return r;
+    }
     for (int p = 0; p < 4; ++p) {
         uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
         r = launch_pass_u32(h, in, out, n, 8 * p, p, s);
@@ -633,15 +682,10 @@ int vkrs_multi_sort_pairs(vkrs_handle h, uint32_t *keys0, uint32_t *keys1, uint3
     if (!keys0 || !keys1 || !values0 || !values1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    constexpr uint32_t tile = PAIR_THREADS * PAIR_KPT;
-    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
-    if (r) return r;
-    r = launch_global_histogram<uint32_t, 4>(h, keys0, n, s);
-    if (r) return r;
     for (int p = 0; p < 4; ++p) {
         uint32_t *in = (p & 1) ? keys1 : keys0, *out = (p & 1) ? keys0 : keys1;
         uint32_t *vin = (p & 1) ? values1 : values0, *vout = (p & 1) ? values0 : values1;
-        r = launch_pass_t<uint32_t, true, PAIR_THREADS, PAIR_KPT, MATCH_PTX, 2>(h, in, out, vin, vout, n, 8 * p, p, s);
+        r = launch_seg_t<uint32_t, true, PAIR_WORKERS, PAIR_KPT, 2, 1>(h, in, out, vin, vout, n, 8 * p, s);
         if (r) return r;
     }
     return VKRS_OK;
@@ -657,15 +701,10 @@ int vkrs_multi_sort_u64(vkrs_handle h, uint64_t *buf0, uint64_t *buf1, uint32_t 
     if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    constexpr uint32_t tile = U64_THREADS * U64_KPT;
-    r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);
-    if (r) return r;
     using K = unsigned long long;
-    r = launch_global_histogram<K, 8>(h, reinterpret_cast<const K *>(buf0), n, s);
-    if (r) return r;
     for (int p = 0; p < 8; ++p) { // NUM_ITERATIONS = 8, MultiRadixSort.cpp:54
         K *in = reinterpret_cast<K *>((p & 1) ? buf1 : buf0), *out = reinterpret_cast<K *>((p & 1) ? buf0 : buf1);
-        r = launch_pass_t<K, false, U64_THREADS, U64_KPT, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, 8 * p, p, s);
+        r = launch_seg_t<K, false, U64_WORKERS, U64_KPT, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s);
         if (r) return r;
     }
     return VKRS_OK;

@@ -55,6 +55,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// Same, for threads that have nothing else to do and share their scheduler with busy warps: one
+// probe, then sleep `ns` before the next, so the waiting warp stays out of the issue slots.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    const uint32_t addr = smem_u32(bar);
+    unsigned long long t_start = 0;
+    for (uint32_t attempt = 0;; ++attempt) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(ns);
+        if ((attempt & 1023u) == 1023u) {
+            const unsigned long long now = global_timer_ns();
+            if (t_start == 0) t_start = now;
+            else if (now - t_start > 10000000000ull) __trap();
+        }
+    }
+}
+
 // 1-D TMA bulk copy: `bytes` (multiple of 16) from 16-byte aligned global memory to 16-byte
 // aligned shared memory; the mbarrier receives complete_tx(bytes) when the data has landed.
 __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {

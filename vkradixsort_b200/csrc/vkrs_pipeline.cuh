@@ -31,7 +31,7 @@ namespace vkrs {
 enum TileMode : uint32_t { TILE_TMA = 0, TILE_MANUAL = 1, TILE_END = 2 };
 
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT>
-struct PipeSmem {
+struct PipeGroupSmem {
     static constexpr int WARPS = WORKERS / 32;
     static constexpr int TILE = WORKERS * KPT;
     alignas(128) KeyT in[2][TILE];                       // TMA destinations (keys of tile j, j+1)
@@ -39,12 +39,24 @@ struct PipeSmem {
     alignas(128) KeyT sorted[TILE];                      // tile in digit order, staged for the write-out
     alignas(128) uint32_t sorted_v[HAS_VALUES ? TILE : 4];
     uint32_t warp_cnt[WARPS][RADIX];                     // per-warp digit counters, then exclusive bases
-    uint32_t count[2][RADIX];                            // tile digit counts for the control warp
+    uint32_t count[2][RADIX];                            // tile digit counts for the control group
     uint32_t lexcl[2][RADIX];                            // start of each digit inside the sorted tile
     uint32_t bin_dst[2][RADIX];                          // global start of the digit run minus lexcl
     uint32_t tile_id[2], tile_mode[2];
     uint32_t scan_scratch[8];
     alignas(8) uint64_t full[2], empty[2], counts_ready[2], prefix_ready[2];
+};
+
+// GROUPS worker groups share one CTA and one control group.  With GROUPS == 2 the groups run the
+// same per-tile loop half a period apart ("ping-pong"): a token (named barriers 6/7) lets only one
+// group at a time into the ALU-bound ranking phase, so one group's ranking overlaps the other's
+// shared-memory-bound scatter / write-out instead of both fighting for the same pipe.
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS>
+struct PipeSmem {
+    using Group = PipeGroupSmem<KeyT, HAS_VALUES, WORKERS, KPT>;
+    static constexpr int WARPS = Group::WARPS;
+    static constexpr int TILE = Group::TILE;
+    Group g[GROUPS];
 };
 
 constexpr int CTRL_THREADS = RADIX; // the control group: one thread per digit (8 warps)
@@ -58,26 +70,31 @@ template <int REGS>
 __device__ __forceinline__ void setmaxnreg_dec() {
     if constexpr (REGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 
 // REG_WORKER / REG_CTRL: per-thread register budgets after the role split (setmaxnreg; 0 = keep
 // the launch allocation).  The control threads give registers back, the workers pick them up.
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int MIN_BLOCKS, int REG_WORKER, int REG_CTRL,
-          int MATCH = MATCH_TABLE>
-__global__ void __launch_bounds__(WORKERS + CTRL_THREADS, MIN_BLOCKS)
+          int MATCH = MATCH_TABLE, int GROUPS = 1>
+__global__ void __launch_bounds__(GROUPS * WORKERS + CTRL_THREADS, MIN_BLOCKS)
 onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                           const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
                           uint32_t shift, const uint32_t *__restrict__ bin_start, uint32_t *status,
                           uint32_t *status_clear, uint32_t *ticket, uint32_t *error_flag,
                           unsigned long long *dbg) {
-    using Smem = PipeSmem<KeyT, HAS_VALUES, WORKERS, KPT>;
+    using Smem = PipeSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     constexpr int WARPS = Smem::WARPS;
     constexpr uint32_t TILE = Smem::TILE;
+    constexpr int ALL_WORKERS = GROUPS * WORKERS;
+    static_assert(GROUPS == 1 || GROUPS == 2, "one worker group, or two in ping-pong");
     static_assert(WORKERS >= RADIX && WORKERS % 128 == 0, "whole warpgroups of workers, one thread per digit");
     static_assert(TILE <= 65536 && KPT % 2 == 0, "tile ranks are stored in 16 bits, two per register");
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t num_tiles = (uint32_t) (((uint64_t) n + TILE - 1) / TILE);
     // TMA needs 16-byte aligned global addresses; tile offsets are multiples of 16 bytes.
     const bool tma_ok = ((reinterpret_cast<uintptr_t>(keys_in) & 15) == 0) &&
@@ -85,22 +102,25 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
 
     if (tid == 0) {
 #pragma unroll
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(&s.full[b], 1);
-            mbar_init(&s.empty[b], WARPS);
-            mbar_init(&s.counts_ready[b], RADIX / 32);
-            mbar_init(&s.prefix_ready[b], CTRL_THREADS / 32);
-        }
+        for (int gi = 0; gi < GROUPS; ++gi)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&sm.g[gi].full[b], 1);
+                mbar_init(&sm.g[gi].empty[b], WARPS);
+                mbar_init(&sm.g[gi].counts_ready[b], RADIX / 32);
+                mbar_init(&sm.g[gi].prefix_ready[b], CTRL_THREADS / 32);
+            }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (tid >= WORKERS) {
+    if (tid >= ALL_WORKERS) {
         // ================================ control group ================================
         setmaxnreg_dec<REG_CTRL>();
-        const uint32_t d = tid - WORKERS; // this thread's digit
-        // Thread 0 of the group claims the next tile and starts its load into ring slot `slot`.
-        auto claim = [&](uint32_t slot) {
+        const uint32_t d = tid - ALL_WORKERS; // this thread's digit
+        // Thread 0 of the group claims the next tile of worker group `s` and starts its load into
+        // ring slot `slot`.
+        auto claim = [&](typename Smem::Group &s, uint32_t slot) {
             const uint32_t t = atomicAdd(ticket, 1u);
             uint32_t mode = TILE_END;
             if (t < num_tiles) {
@@ -123,34 +143,51 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
 
         // phase timers (tuning aid, only when dbg != nullptr): cycles of control thread 0
         unsigned long long t_counts = 0, t_claim = 0, t_look = 0, n_tiles = 0, t0 = 0;
-        if (d == 0) claim(0);
-        named_bar_sync(3, CTRL_THREADS);
-        uint32_t mode = s.tile_mode[0], tile = s.tile_id[0];
-        for (uint32_t j = 0; mode != TILE_END; ++j) {
-            const uint32_t slot = j & 1, par = (j >> 1) & 1;
-            if (dbg) t0 = clock64();
-            mbar_wait(&s.counts_ready[slot], par);
-            if (dbg) { const unsigned long long t1 = clock64(); t_counts += t1 - t0; t0 = t1; }
-            // Claim tile j+1 only now, a fixed distance (scatter of j + ranking of j+1) ahead of
-            // the moment its own counts will be published: a ticket taken earlier would sit
-            // unpublished for a variable time and stall every later tile's look-back.  The other
-            // ring slot was drained by the scatter of tile j-1, long ago.
-            if (d == 0) {
-                if (j >= 1) mbar_wait(&s.empty[slot ^ 1], ((j - 1) >> 1) & 1);
-                claim(slot ^ 1);
-                if (dbg) { const unsigned long long t1 = clock64(); t_claim += t1 - t0; t0 = t1; }
+        if (d == 0) {
+#pragma unroll
+            for (int gi = 0; gi < GROUPS; ++gi) claim(sm.g[gi], 0);
+        }
+        named_bar_sync(5, CTRL_THREADS);
+        uint32_t mode[GROUPS], tile[GROUPS];
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) {
+            mode[gi] = sm.g[gi].tile_mode[0];
+            tile[gi] = sm.g[gi].tile_id[0];
+        }
+        // The worker groups take turns, so their tiles reach the control group alternately too.
+        for (uint32_t j = 0;; ++j) {
+            bool any = false;
+#pragma unroll
+            for (int gi = 0; gi < GROUPS; ++gi) {
+                if (mode[gi] == TILE_END) continue;
+                any = true;
+                typename Smem::Group &s = sm.g[gi];
+                const uint32_t slot = j & 1, par = (j >> 1) & 1;
+                if (dbg) t0 = clock64();
+                mbar_wait_sleep(&s.counts_ready[slot], par, 128);
+                if (dbg) { const unsigned long long t1 = clock64(); t_counts += t1 - t0; t0 = t1; }
+                // Claim tile j+1 only now, a fixed distance (scatter of j + ranking of j+1) ahead of
+                // the moment its own counts will be published: a ticket taken earlier would sit
+                // unpublished for a variable time and stall every later tile's look-back.  The
+                // other ring slot was drained by the scatter of tile j-1, long ago.
+                if (d == 0) {
+                    if (j >= 1) mbar_wait(&s.empty[slot ^ 1], ((j - 1) >> 1) & 1);
+                    claim(s, slot ^ 1);
+                    if (dbg) { const unsigned long long t1 = clock64(); t_claim += t1 - t0; t0 = t1; }
+                }
+                // ---- chained scan of tile j, this thread's digit ----
+                const uint32_t cnt = s.count[slot][d];
+                const ChainedScanBase base{status, status_clear, bin_start, error_flag, tile[gi]};
+                base.publish(d, cnt);
+                s.bin_dst[slot][d] = base.template resolve<CTRL_WINDOW, 100>(d, cnt) - s.lexcl[slot][d];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.prefix_ready[slot]);
+                if (dbg) { t_look += clock64() - t0; n_tiles++; }
+                named_bar_sync(5, CTRL_THREADS); // thread 0's claim is visible to the group
+                mode[gi] = s.tile_mode[slot ^ 1];
+                tile[gi] = s.tile_id[slot ^ 1];
             }
-            // ---- chained scan of tile j, this thread's digit ----
-            const uint32_t cnt = s.count[slot][d];
-            const ChainedScanBase base{status, status_clear, bin_start, error_flag, tile};
-            base.publish(d, cnt);
-            s.bin_dst[slot][d] = base.template resolve<CTRL_WINDOW, 100>(d, cnt) - s.lexcl[slot][d];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s.prefix_ready[slot]);
-            if (dbg) { t_look += clock64() - t0; n_tiles++; }
-            named_bar_sync(3, CTRL_THREADS); // thread 0's claim is visible to the group
-            mode = s.tile_mode[slot ^ 1];
-            tile = s.tile_id[slot ^ 1];
+            if (!any) break;
         }
         if (dbg && d == 0) {
             atomicAdd(dbg + 0, t_counts);
@@ -163,6 +200,11 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
 
     setmaxnreg_inc<REG_WORKER>();
     // ==================================== workers ====================================
+    const int grp = GROUPS == 1 ? 0 : tid / WORKERS;
+    const int gtid = tid - grp * WORKERS, warp = gtid >> 5;
+    typename Smem::Group &s = sm.g[grp];
+    const uint32_t bar_w = 1 + grp, bar_d = 3 + grp;       // this group's worker / digit barriers
+    const uint32_t tok_mine = 6 + grp, tok_other = 7 - grp; // ranking tokens (GROUPS == 2)
     const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
     const DigitBitMasks bm(sizeof(KeyT) == 8 ? (shift & 31u) : shift);
     const LaneNibbleConsts lc(lane);
@@ -176,7 +218,7 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
     // phase timers of worker warp 0 (tuning aid): wait-for-tile, rank, barrier A, digit section,
     // wait-for-prefix, write-out, barrier B, scatter
     unsigned long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
-    const bool timing = dbg != nullptr && warp == 0;
+    const bool timing = dbg != nullptr && tid < 32;
 #define VKRS_PHASE(k)                                \
     if (timing) {                                    \
         const unsigned long long tn = clock64();     \
@@ -188,7 +230,7 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
         const bool full = valid == TILE;
 #pragma unroll
         for (int jj = 0; jj < KPT; ++jj) {
-            const uint32_t p = tid + jj * WORKERS;
+            const uint32_t p = gtid + jj * WORKERS;
             const KeyT k = s.sorted[p];
             const uint32_t g = s.bin_dst[pslot][digit_prmt(key_word(k), dsel)] + p;
             if (full || p < valid) {
@@ -203,7 +245,6 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
         const uint32_t slot = j & 1, par = (j >> 1) & 1;
         if (timing) tp = clock64();
         mbar_wait(&s.full[slot], par);
-        VKRS_PHASE(0)
         const uint32_t mode = s.tile_mode[slot];
         if (mode == TILE_END) break;
         const uint32_t tile = s.tile_id[slot];
@@ -214,12 +255,15 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
             // Partial last tile or a buffer TMA cannot address: the workers copy it in.  Missing
             // keys become all-ones: digit 255 at every shift and last in memory order, so they
             // rank after every real key, at tile positions >= valid.
-            for (uint32_t p = tid; p < TILE; p += WORKERS) {
+            for (uint32_t p = gtid; p < TILE; p += WORKERS) {
                 s.in[slot][p] = p < valid ? ld_stream(keys_in + tile_base + p) : ~KeyT(0);
                 if (HAS_VALUES) s.vin[slot][p] = p < valid ? ld_stream(vals_in + tile_base + p) : 0u;
             }
-            named_bar_sync(1, WORKERS);
+            named_bar_sync(bar_w, WORKERS);
         }
+        // ---- ping-pong: wait for the other group to leave the ranking phase ----
+        if (GROUPS == 2 && (grp == 1 || j > 0)) named_bar_sync(tok_mine, ALL_WORKERS);
+        VKRS_PHASE(0)
 
         // ---- rank inside the warp (see vkrs_tile.cuh for the protocol) ----
 #pragma unroll
@@ -237,19 +281,20 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
             else rank2[i / 2] = r;
             __syncwarp();
         }
+        if (GROUPS == 2) named_bar_arrive(tok_other, ALL_WORKERS); // the other group may rank now
         VKRS_PHASE(1)
-        named_bar_sync(1, WORKERS); // (A) all warp counters final; sorted[] holds tile j-1 completely
+        named_bar_sync(bar_w, WORKERS); // (A) all warp counters final; sorted[] holds tile j-1 completely
         VKRS_PHASE(2)
 
-        // ---- digit threads: tile counts to the control warp, tile-local scan, warp bases ----
-        if (tid < RADIX) {
+        // ---- digit threads: tile counts to the control group, tile-local scan, warp bases ----
+        if (gtid < RADIX) {
             uint32_t total = 0;
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) total += s.warp_cnt[w][tid];
-            // block-wide exclusive scan over the 256 digit threads (named barrier 2)
+            for (int w = 0; w < WARPS; ++w) total += s.warp_cnt[w][gtid];
+            // block-wide exclusive scan over the 256 digit threads
             const uint32_t incl = warp_inclusive_scan(total, lane);
             if (lane == 31) s.scan_scratch[warp] = incl;
-            named_bar_sync(2, RADIX);
+            named_bar_sync(bar_d, RADIX);
             uint32_t warp_prefix = 0;
 #pragma unroll
             for (int w = 0; w < RADIX / 32; ++w)
@@ -258,13 +303,13 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
             uint32_t running = local_excl;
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = s.warp_cnt[w][tid];
-                s.warp_cnt[w][tid] = running;
+                const uint32_t c = s.warp_cnt[w][gtid];
+                s.warp_cnt[w][gtid] = running;
                 running += c;
             }
             // what the rest of the grid must see: real keys only (padding sits in digit 255)
-            s.count[slot][tid] = (valid != TILE && tid == RADIX - 1) ? total - (TILE - valid) : total;
-            s.lexcl[slot][tid] = local_excl;
+            s.count[slot][gtid] = (valid != TILE && gtid == RADIX - 1) ? total - (TILE - valid) : total;
+            s.lexcl[slot][gtid] = local_excl;
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.counts_ready[slot]);
         }
@@ -277,29 +322,51 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
             write_out(slot ^ 1, prev_valid);
         }
         VKRS_PHASE(5)
-        named_bar_sync(1, WORKERS); // (B) warp bases of tile j ready; sorted[] free
+        named_bar_sync(bar_w, WORKERS); // (B) warp bases of tile j ready; sorted[] free
         VKRS_PHASE(6)
 
         // ---- keys (and payloads) of tile j to their rank in the staging buffer ----
+        // In batches, all loads of a batch before its stores: the three shared-memory accesses
+        // per key are latency-bound if they run key by key.
+        constexpr int SB = KPT % 8 == 0 ? 8 : (KPT % 4 == 0 ? 4 : 2);
 #pragma unroll
-        for (int i = 0; i < KPT; ++i) {
-            const KeyT key = tin[chunk0 + i * 32];
-            const uint32_t r = ((i & 1) ? (rank2[i / 2] >> 16) : (rank2[i / 2] & 0xffffu)) + my_cnt[digit_prmt(key_word(key), dsel)];
-            s.sorted[r] = key;
-            if (HAS_VALUES) s.sorted_v[r] = s.vin[slot][chunk0 + i * 32];
+        for (int i0 = 0; i0 < KPT; i0 += SB) {
+            KeyT kb[SB];
+            uint32_t rb[SB];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) kb[i] = tin[chunk0 + (i0 + i) * 32];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) rb[i] = my_cnt[digit_prmt(key_word(kb[i]), dsel)];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                const int k = i0 + i;
+                rb[i] += (k & 1) ? (rank2[k / 2] >> 16) : (rank2[k / 2] & 0xffffu);
+            }
+#pragma unroll
+            for (int i = 0; i < SB; ++i) s.sorted[rb[i]] = kb[i];
+            if (HAS_VALUES) {
+                uint32_t vb[SB];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) vb[i] = s.vin[slot][chunk0 + (i0 + i) * 32];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) s.sorted_v[rb[i]] = vb[i];
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&s.empty[slot]); // ring slot may be refilled
         VKRS_PHASE(7)
         prev_valid = valid;
     }
+    // Out of tiles.  The other group may still hold one claimed tile: hand it the ranking token a
+    // last time (see the header comment; pending arrivals on a named barrier are harmless at exit).
+    if (GROUPS == 2) named_bar_arrive(tok_other, ALL_WORKERS);
     if (timing && lane == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(dbg + 8 + k, tw[k]);
     }
 #undef VKRS_PHASE
-    if (j > 0) { // drain: the last tile this CTA ranked
-        named_bar_sync(1, WORKERS);
+    if (j > 0) { // drain: the last tile this group ranked
+        named_bar_sync(bar_w, WORKERS);
         mbar_wait(&s.prefix_ready[(j - 1) & 1], ((j - 1) >> 1) & 1);
         write_out((j - 1) & 1, prev_valid);
     }

@@ -1,0 +1,403 @@
+// vkrs_segmented.cuh -- the segmented two-kernel digit pass: the reference's own decomposition
+// (multi_radixsort_histograms.comp + multi_radixsort.comp) re-tiled for B200.
+//
+//   segment_histogram_kernel   CTA g counts the digits of segment g (a contiguous slab of tiles,
+//                              exactly the reference's "work group w owns nb*256 consecutive keys")
+//                              into row g of the histogram matrix.  One coalesced read of the keys.
+//   segmented_scatter_kernel   persistent CTA, two worker groups, group g owns segment g.  Prologue:
+//                              offsets[g][d] = sum_{d'<d} sum_{g'} hist[g'][d'] + sum_{g'<g} hist[g'][d]
+//                              (multi_radixsort.comp:56-77) with G = 2 x #SMs rows instead of the
+//                              reference's W = N/(nb*256).  Then the group walks its segment tile by
+//                              tile with running per-digit offsets (global_offsets[], :120-122): TMA
+//                              double-buffered loads, warp-private stable ranking, a shared-memory
+//                              reorder and coalesced write-out.
+//
+// Why not the single-sweep chained scan here: on B200 a tile retires every ~20 ns across the chip
+// while one L2 round trip takes ~500 ns, so every tile's look-back has to cover dozens of
+// predecessors; the chain, not the data path, sets the pace (measured: 0.43 ms/pass however the
+// tiles are shaped).  Counting first costs one extra 4 B/key read per pass and removes every
+// inter-CTA dependency from the scatter.  A CTA hosts GROUPS independent worker groups (own segment,
+// own ring, own named barriers): while one group is in the ALU-bound ranking phase another is in its
+// shared-memory-bound scatter / write-out, so the phases of different groups overlap on the SM.
+// (An explicit ping-pong token between two groups was measured slower than letting them drift.)
+#pragma once
+#include "vkrs_async.cuh"
+#include "vkrs_common.cuh"
+
+namespace vkrs {
+
+// Tiles [first, first + count) of segment g when `num_tiles` tiles are dealt to `num_segments`
+// segments as evenly as possible (host and device agree through this one function).
+__host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_segments, uint32_t num_tiles,
+                                                       uint32_t &first, uint32_t &count) {
+    const uint32_t q = num_tiles / num_segments, r = num_tiles % num_segments;
+    first = g * q + (g < r ? g : r);
+    count = q + (g < r ? 1u : 0u);
+}
+
+// =====================================================================================
+// Kernel 1: hist[g][d] = #{keys of segment g with digit d}.  Grid = number of segments.
+// Shared-memory counters are lane-private columns of packed 16-bit halves (bank == lane: one
+// wavefront per atomic whatever the key distribution); a column is folded into the thread totals
+// before it could overflow.
+// =====================================================================================
+constexpr int SEGHIST_THREADS = 512;
+constexpr uint32_t SEGHIST_FLUSH_KEYS = 1u << 20; // 2^20 keys / 32 lanes = 32768 per column < 65536
+
+template <typename KeyT>
+__global__ void __launch_bounds__(SEGHIST_THREADS)
+segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t tile_keys,
+                         uint32_t num_tiles, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t cnt[128 * 32]; // [digit >> 1][lane], half (digit & 1)
+    const int tid = threadIdx.x, lane = tid & 31;
+    uint32_t first, count;
+    segment_tiles(blockIdx.x, gridDim.x, num_tiles, first, count);
+    const uint64_t lo = (uint64_t) first * tile_keys;
+    uint64_t hi = lo + (uint64_t) count * tile_keys;
+    if (hi > n) hi = n;
+    const uint32_t wshift = sizeof(KeyT) == 8 ? (shift & 32u) : 0u;
+    const uint32_t dsel = digit_selector(shift);
+    auto count_key = [&](KeyT k) {
+        const uint32_t d = digit_prmt((uint32_t) ((uint64_t) k >> wshift), dsel);
+        atomicAdd(&cnt[(d >> 1) * 32 + lane], (d & 1u) ? 0x10000u : 1u);
+    };
+    uint32_t total = 0; // digit `tid` (threads 0..255)
+    for (uint64_t c0 = lo; c0 < hi || c0 == lo; c0 += SEGHIST_FLUSH_KEYS) {
+        for (int i = tid; i < 128 * 32; i += SEGHIST_THREADS) cnt[i] = 0;
+        __syncthreads();
+        const uint64_t c1 = (c0 + SEGHIST_FLUSH_KEYS < hi) ? c0 + SEGHIST_FLUSH_KEYS : hi;
+        if (c0 < c1) {
+            constexpr int VEC = 16 / sizeof(KeyT);
+            const KeyT *base = keys + c0;
+            const uint64_t cnt_keys = c1 - c0;
+            uint64_t head = ((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) / sizeof(KeyT);
+            if (head > cnt_keys) head = cnt_keys;
+            const uint64_t nvec = (cnt_keys - head) / VEC;
+            if (tid < head) count_key(base[tid]);
+            const uint4 *vbase = reinterpret_cast<const uint4 *>(base + head);
+            uint64_t v = tid;
+            for (; v + 3 * SEGHIST_THREADS < nvec; v += 4 * SEGHIST_THREADS) { // four 128-bit loads in flight
+                uint4 a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = ld_stream(vbase + v + u * SEGHIST_THREADS);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (sizeof(KeyT) == 4) {
+                        count_key((KeyT) a[u].x); count_key((KeyT) a[u].y); count_key((KeyT) a[u].z); count_key((KeyT) a[u].w);
+                    } else {
+                        count_key((KeyT) (((uint64_t) a[u].y << 32) | a[u].x));
+                        count_key((KeyT) (((uint64_t) a[u].w << 32) | a[u].z));
+                    }
+                }
+            }
+            for (; v < nvec; v += SEGHIST_THREADS) {
+                const uint4 a = ld_stream(vbase + v);
+                if (sizeof(KeyT) == 4) {
+                    count_key((KeyT) a.x); count_key((KeyT) a.y); count_key((KeyT) a.z); count_key((KeyT) a.w);
+                } else {
+                    count_key((KeyT) (((uint64_t) a.y << 32) | a.x)); count_key((KeyT) (((uint64_t) a.w << 32) | a.z));
+                }
+            }
+            const uint64_t tail0 = head + nvec * VEC;
+            if (tail0 + tid < cnt_keys) count_key(base[tail0 + tid]);
+        }
+        __syncthreads();
+        if (tid < RADIX) {
+            const uint32_t *row = &cnt[(tid >> 1) * 32];
+            const uint32_t sh = (tid & 1) * 16;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) total += (row[(j + (tid >> 1)) & 31] >> sh) & 0xffffu; // skewed: conflict-free
+        }
+        __syncthreads();
+    }
+    if (tid < RADIX) hist[(size_t) blockIdx.x * RADIX + tid] = total;
+}
+
+// =====================================================================================
+// Kernel 2: the scatter.  GROUPS * WORKERS worker threads + one producer warp.
+// =====================================================================================
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT>
+struct SegGroupSmem {
+    static constexpr int WARPS = WORKERS / 32;
+    static constexpr int TILE = WORKERS * KPT;
+    alignas(128) KeyT in[2][TILE];                       // TMA destinations (tile j, j+1 of the segment)
+    alignas(128) uint32_t vin[HAS_VALUES ? 2 : 1][HAS_VALUES ? TILE : 4];
+    alignas(128) KeyT sorted[TILE];                      // tile in digit order, staged for the write-out
+    alignas(128) uint32_t sorted_v[HAS_VALUES ? TILE : 4];
+    uint32_t warp_cnt[WARPS][RADIX];                     // per-warp digit counters, then exclusive bases
+    uint32_t bin_dst[2][RADIX];                          // global start of the digit run minus its start in the tile
+    uint32_t scan_scratch[8];
+    alignas(8) uint64_t full[2], empty[2];
+};
+
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS>
+struct SegSmem {
+    using Group = SegGroupSmem<KeyT, HAS_VALUES, WORKERS, KPT>;
+    Group g[GROUPS];
+};
+
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
+segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
+                         const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
+                         uint32_t shift, const uint32_t *__restrict__ hist, uint32_t num_tiles,
+                         unsigned long long *dbg) {
+    using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
+    using Group = typename Smem::Group;
+    constexpr int WARPS = Group::WARPS;
+    constexpr uint32_t TILE = Group::TILE;
+    constexpr int ALL_WORKERS = GROUPS * WORKERS;
+    static_assert(GROUPS >= 1 && GROUPS <= 4, "1..4 worker groups per CTA");
+    static_assert(WORKERS >= RADIX && WORKERS % 32 == 0, "one worker thread per digit is required");
+    static_assert(TILE <= 65536 && KPT % 2 == 0, "tile ranks are stored in 16 bits, two per register");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t num_segments = gridDim.x * GROUPS;
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(keys_in) & 15) == 0) &&
+                        (!HAS_VALUES || (reinterpret_cast<uintptr_t>(vals_in) & 15) == 0);
+
+    if (tid == 0) {
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&sm.g[gi].full[b], 1);
+                mbar_init(&sm.g[gi].empty[b], WARPS);
+            }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // A tile can go through TMA when it is full and its global address is 16-byte aligned.
+    auto tile_is_tma = [&](uint32_t tile) { return tma_ok && (uint64_t) n - (uint64_t) tile * TILE >= TILE; };
+
+    if (tid >= ALL_WORKERS) {
+        // ============================ producer warp (lane 0) ============================
+        if (lane != 0) return;
+        uint32_t first[GROUPS], count[GROUPS];
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) segment_tiles(blockIdx.x * GROUPS + gi, num_segments, num_tiles, first[gi], count[gi]);
+        uint32_t max_count = 0;
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) max_count = count[gi] > max_count ? count[gi] : max_count;
+        for (uint32_t j = 0; j < max_count; ++j) {
+#pragma unroll
+            for (int gi = 0; gi < GROUPS; ++gi) {
+                if (j >= count[gi]) continue;
+                Group &s = sm.g[gi];
+                const uint32_t slot = j & 1, tile = first[gi] + j;
+                if (j >= 2) mbar_wait_sleep(&s.empty[slot], ((j - 2) >> 1) & 1, 64); // tile j-2 fully consumed
+                if (tile_is_tma(tile)) {
+                    const uint64_t base = (uint64_t) tile * TILE;
+                    constexpr uint32_t kbytes = TILE * sizeof(KeyT);
+                    mbar_arrive_expect_tx(&s.full[slot], kbytes + (HAS_VALUES ? TILE * 4u : 0u));
+                    bulk_copy_g2s(s.in[slot], keys_in + base, kbytes, &s.full[slot]);
+                    if (HAS_VALUES) bulk_copy_g2s(s.vin[slot], vals_in + base, TILE * 4u, &s.full[slot]);
+                } else {
+                    mbar_arrive(&s.full[slot]); // the workers copy this tile in themselves
+                }
+            }
+        }
+        return;
+    }
+
+    // ==================================== workers ====================================
+    const int grp = GROUPS == 1 ? 0 : tid / WORKERS;
+    const int gtid = tid - grp * WORKERS, warp = gtid >> 5;
+    Group &s = sm.g[grp];
+    const uint32_t seg = blockIdx.x * GROUPS + grp;
+    uint32_t first_tile, tile_count;
+    segment_tiles(seg, num_segments, num_tiles, first_tile, tile_count);
+    const uint32_t bar_w = 1 + grp, bar_d = 1 + GROUPS + grp; // this group's worker / digit named barriers
+    const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
+    const DigitBitMasks bm(sizeof(KeyT) == 8 ? (shift & 31u) : shift);
+    const LaneNibbleConsts lc(lane);
+    const uint32_t dsel = digit_selector(shift);
+    auto key_word = [&](KeyT key) -> uint32_t { // the 32-bit word of the key that holds the digit
+        return sizeof(KeyT) == 8 ? (uint32_t) ((uint64_t) key >> (shift & 32u)) : (uint32_t) key;
+    };
+    uint32_t *my_cnt = s.warp_cnt[warp];
+    const uint32_t chunk0 = warp * (KPT * 32) + lane; // warp-striped: lane l holds chunk[i*32 + l]
+
+    // ---- prologue (multi_radixsort.comp:56-77): this segment's first output index per digit ----
+    uint32_t running_base = 0; // digit thread `gtid`: where the next tile's run of that digit starts
+    if (gtid < RADIX) {
+        uint32_t below = 0, total = 0;
+        uint32_t g2 = 0;
+        for (; g2 + 8 <= num_segments; g2 += 8) { // eight independent loads in flight
+            uint32_t h[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) h[u] = __ldcg(hist + (size_t) (g2 + u) * RADIX + gtid);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                total += h[u];
+                if (g2 + u < seg) below += h[u];
+            }
+        }
+        for (; g2 < num_segments; ++g2) {
+            const uint32_t h = __ldcg(hist + (size_t) g2 * RADIX + gtid);
+            total += h;
+            if (g2 < seg) below += h;
+        }
+        const uint32_t incl = warp_inclusive_scan(total, lane);
+        if (lane == 31) s.scan_scratch[warp] = incl;
+        named_bar_sync(bar_d, RADIX);
+        uint32_t warp_prefix = 0;
+#pragma unroll
+        for (int w = 0; w < RADIX / 32; ++w)
+            if (w < warp) warp_prefix += s.scan_scratch[w];
+        running_base = warp_prefix + incl - total + below;
+        named_bar_sync(bar_d, RADIX); // scan_scratch is reused by the per-tile scan
+    }
+
+    // phase timers of worker warp 0 (tuning aid): wait-for-tile(+token), rank, barrier A, digit
+    // section, -, write-out, barrier B, scatter
+    unsigned long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = 0;
+    const bool timing = dbg != nullptr && tid < 32;
+#define VKRS_PHASE(k)                                \
+    if (timing) {                                    \
+        const unsigned long long tn = clock64();     \
+        tw[k] += tn - tp;                            \
+        tp = tn;                                     \
+    }
+
+    auto write_out = [&](uint32_t pslot, uint32_t valid) {
+        const bool full = valid == TILE;
+#pragma unroll
+        for (int jj = 0; jj < KPT; ++jj) {
+            const uint32_t p = gtid + jj * WORKERS;
+            const KeyT k = s.sorted[p];
+            const uint32_t g = s.bin_dst[pslot][digit_prmt(key_word(k), dsel)] + p;
+            if (full || p < valid) {
+                keys_out[g] = k;
+                if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
+            }
+        }
+    };
+
+    uint32_t prev_valid = 0;
+    for (uint32_t j = 0; j < tile_count; ++j) {
+        const uint32_t slot = j & 1, par = (j >> 1) & 1;
+        const uint32_t tile = first_tile + j;
+        const uint64_t tile_base = (uint64_t) tile * TILE;
+        const uint32_t valid = ((uint64_t) n - tile_base < TILE) ? (uint32_t) (n - tile_base) : TILE;
+        const KeyT *tin = s.in[slot];
+        if (timing) tp = clock64();
+        mbar_wait(&s.full[slot], par);
+        if (!tile_is_tma(tile)) {
+            // Partial last tile or a buffer TMA cannot address: the workers copy it in.  Missing
+            // keys become all-ones: digit 255 at every shift and last in memory order, so they
+            // rank after every real key, at tile positions >= valid.
+            for (uint32_t p = gtid; p < TILE; p += WORKERS) {
+                s.in[slot][p] = p < valid ? ld_stream(keys_in + tile_base + p) : ~KeyT(0);
+                if (HAS_VALUES) s.vin[slot][p] = p < valid ? ld_stream(vals_in + tile_base + p) : 0u;
+            }
+            named_bar_sync(bar_w, WORKERS);
+        }
+        VKRS_PHASE(0)
+
+        // ---- rank inside the warp (protocol: see vkrs_tile.cuh) ----
+#pragma unroll
+        for (int q = 0; q < RADIX / 32; ++q) my_cnt[lane + 32 * q] = 0;
+        __syncwarp();
+        uint32_t rank2[KPT / 2];
+        // Software-pipelined: the ballots of round i+1 are issued before the counter update of
+        // round i, so the shared-memory round trip of one round hides behind the votes of the next.
+        uint32_t d_cur = digit_prmt(key_word(tin[chunk0]), dsel);
+        uint32_t peers_cur = match_key_table(key_word(tin[chunk0]), d_cur, bm, lc);
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            uint32_t d_next = 0, peers_next = 0;
+            if (i + 1 < KPT) {
+                const uint32_t word = key_word(tin[chunk0 + (i + 1) * 32]);
+                d_next = digit_prmt(word, dsel);
+                peers_next = match_key_table(word, d_next, bm, lc);
+            }
+            const uint32_t r = my_cnt[d_cur] + __popc(peers_cur & lt_mask);
+            if ((peers_cur & gt_mask) == 0) my_cnt[d_cur] = r + 1; // highest lane of the group
+            if (i & 1) rank2[i / 2] |= r << 16;
+            else rank2[i / 2] = r;
+            __syncwarp();
+            d_cur = d_next;
+            peers_cur = peers_next;
+        }
+        VKRS_PHASE(1)
+        named_bar_sync(bar_w, WORKERS); // (A) all warp counters final; sorted[] holds tile j-1 completely
+        VKRS_PHASE(2)
+
+        // ---- digit threads: tile-local scan, warp bases, this tile's global digit bases ----
+        if (gtid < RADIX) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) total += s.warp_cnt[w][gtid];
+            const uint32_t incl = warp_inclusive_scan(total, lane);
+            if (lane == 31) s.scan_scratch[warp] = incl;
+            named_bar_sync(bar_d, RADIX);
+            uint32_t warp_prefix = 0;
+#pragma unroll
+            for (int w = 0; w < RADIX / 32; ++w)
+                if (w < warp) warp_prefix += s.scan_scratch[w];
+            const uint32_t local_excl = warp_prefix + incl - total;
+            uint32_t running = local_excl;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s.warp_cnt[w][gtid];
+                s.warp_cnt[w][gtid] = running;
+                running += c;
+            }
+            s.bin_dst[slot][gtid] = running_base - local_excl;
+            // real keys only: the padding of a partial tile sits in digit 255
+            running_base += (valid != TILE && gtid == RADIX - 1) ? total - (TILE - valid) : total;
+        }
+        VKRS_PHASE(3)
+        // ---- write tile j-1 out (overlaps the digit threads' work above) ----
+        if (j > 0) write_out(slot ^ 1, prev_valid);
+        VKRS_PHASE(5)
+        named_bar_sync(bar_w, WORKERS); // (B) warp bases and bin_dst of tile j ready; sorted[] free
+        VKRS_PHASE(6)
+
+        // ---- keys (and payloads) of tile j to their rank in the staging buffer ----
+        constexpr int SB = KPT % 8 == 0 ? 8 : (KPT % 4 == 0 ? 4 : 2);
+#pragma unroll
+        for (int i0 = 0; i0 < KPT; i0 += SB) {
+            KeyT kb[SB];
+            uint32_t rb[SB];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) kb[i] = tin[chunk0 + (i0 + i) * 32];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) rb[i] = my_cnt[digit_prmt(key_word(kb[i]), dsel)];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                const int k = i0 + i;
+                rb[i] += (k & 1) ? (rank2[k / 2] >> 16) : (rank2[k / 2] & 0xffffu);
+            }
+#pragma unroll
+            for (int i = 0; i < SB; ++i) s.sorted[rb[i]] = kb[i];
+            if (HAS_VALUES) {
+                uint32_t vb[SB];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) vb[i] = s.vin[slot][chunk0 + (i0 + i) * 32];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) s.sorted_v[rb[i]] = vb[i];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s.empty[slot]); // ring slot may be refilled
+        VKRS_PHASE(7)
+        prev_valid = valid;
+    }
+    if (timing && lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(dbg + 8 + k, tw[k]);
+        atomicAdd(dbg + 4, (unsigned long long) tile_count);
+    }
+#undef VKRS_PHASE
+    if (tile_count > 0) { // drain: the last tile of the segment
+        named_bar_sync(bar_w, WORKERS);
+        write_out((tile_count - 1) & 1, prev_valid);
+    }
+}
+
+} // namespace vkrs
