@@ -37,18 +37,16 @@ __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_
 
 // =====================================================================================
 // Kernel 1: hist[g][d] = #{keys of segment g with digit d}.  Grid = number of segments.
-// Shared-memory counters are lane-private columns of packed 16-bit halves (bank == lane: one
-// wavefront per atomic whatever the key distribution); a column is folded into the thread totals
-// before it could overflow.
+// Shared-memory counters are lane-private 32-bit columns (bank == lane: one wavefront per atomic
+// whatever the key distribution, all-equal keys included).
 // =====================================================================================
 constexpr int SEGHIST_THREADS = 512;
-constexpr uint32_t SEGHIST_FLUSH_KEYS = 1u << 20; // 2^20 keys / 32 lanes = 32768 per column < 65536
 
 template <typename KeyT>
 __global__ void __launch_bounds__(SEGHIST_THREADS)
 segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t tile_keys,
                          uint32_t num_tiles, uint32_t *__restrict__ hist) {
-    __shared__ uint32_t cnt[128 * 32]; // [digit >> 1][lane], half (digit & 1)
+    __shared__ uint32_t cnt[RADIX * 32]; // [digit][lane]: bank == lane, one wavefront per atomic
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t first, count;
     segment_tiles(blockIdx.x, gridDim.x, num_tiles, first, count);
@@ -57,60 +55,55 @@ segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shi
     if (hi > n) hi = n;
     const uint32_t wshift = sizeof(KeyT) == 8 ? (shift & 32u) : 0u;
     const uint32_t dsel = digit_selector(shift);
+    uint32_t *my_col = cnt + lane;
     auto count_key = [&](KeyT k) {
-        const uint32_t d = digit_prmt((uint32_t) ((uint64_t) k >> wshift), dsel);
-        atomicAdd(&cnt[(d >> 1) * 32 + lane], (d & 1u) ? 0x10000u : 1u);
+        atomicAdd(my_col + digit_prmt((uint32_t) ((uint64_t) k >> wshift), dsel) * 32, 1u);
     };
-    uint32_t total = 0; // digit `tid` (threads 0..255)
-    for (uint64_t c0 = lo; c0 < hi || c0 == lo; c0 += SEGHIST_FLUSH_KEYS) {
-        for (int i = tid; i < 128 * 32; i += SEGHIST_THREADS) cnt[i] = 0;
-        __syncthreads();
-        const uint64_t c1 = (c0 + SEGHIST_FLUSH_KEYS < hi) ? c0 + SEGHIST_FLUSH_KEYS : hi;
-        if (c0 < c1) {
-            constexpr int VEC = 16 / sizeof(KeyT);
-            const KeyT *base = keys + c0;
-            const uint64_t cnt_keys = c1 - c0;
-            uint64_t head = ((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) / sizeof(KeyT);
-            if (head > cnt_keys) head = cnt_keys;
-            const uint64_t nvec = (cnt_keys - head) / VEC;
-            if (tid < head) count_key(base[tid]);
-            const uint4 *vbase = reinterpret_cast<const uint4 *>(base + head);
-            uint64_t v = tid;
-            for (; v + 3 * SEGHIST_THREADS < nvec; v += 4 * SEGHIST_THREADS) { // four 128-bit loads in flight
-                uint4 a[4];
+    for (int i = tid; i < RADIX * 32; i += SEGHIST_THREADS) cnt[i] = 0;
+    __syncthreads();
+    if (lo < hi) {
+        constexpr int VEC = 16 / sizeof(KeyT);
+        const KeyT *base = keys + lo;
+        const uint64_t cnt_keys = hi - lo;
+        uint64_t head = ((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) / sizeof(KeyT);
+        if (head > cnt_keys) head = cnt_keys;
+        const uint64_t nvec = (cnt_keys - head) / VEC;
+        if (tid < head) count_key(base[tid]);
+        const uint4 *vbase = reinterpret_cast<const uint4 *>(base + head);
+        uint64_t v = tid;
+        for (; v + 3 * SEGHIST_THREADS < nvec; v += 4 * SEGHIST_THREADS) { // four 128-bit loads in flight
+            uint4 a[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = ld_stream(vbase + v + u * SEGHIST_THREADS);
+            for (int u = 0; u < 4; ++u) a[u] = ld_stream(vbase + v + u * SEGHIST_THREADS);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (sizeof(KeyT) == 4) {
-                        count_key((KeyT) a[u].x); count_key((KeyT) a[u].y); count_key((KeyT) a[u].z); count_key((KeyT) a[u].w);
-                    } else {
-                        count_key((KeyT) (((uint64_t) a[u].y << 32) | a[u].x));
-                        count_key((KeyT) (((uint64_t) a[u].w << 32) | a[u].z));
-                    }
-                }
-            }
-            for (; v < nvec; v += SEGHIST_THREADS) {
-                const uint4 a = ld_stream(vbase + v);
+            for (int u = 0; u < 4; ++u) {
                 if (sizeof(KeyT) == 4) {
-                    count_key((KeyT) a.x); count_key((KeyT) a.y); count_key((KeyT) a.z); count_key((KeyT) a.w);
+                    count_key((KeyT) a[u].x); count_key((KeyT) a[u].y); count_key((KeyT) a[u].z); count_key((KeyT) a[u].w);
                 } else {
-                    count_key((KeyT) (((uint64_t) a.y << 32) | a.x)); count_key((KeyT) (((uint64_t) a.w << 32) | a.z));
+                    count_key((KeyT) (((uint64_t) a[u].y << 32) | a[u].x));
+                    count_key((KeyT) (((uint64_t) a[u].w << 32) | a[u].z));
                 }
             }
-            const uint64_t tail0 = head + nvec * VEC;
-            if (tail0 + tid < cnt_keys) count_key(base[tail0 + tid]);
         }
-        __syncthreads();
-        if (tid < RADIX) {
-            const uint32_t *row = &cnt[(tid >> 1) * 32];
-            const uint32_t sh = (tid & 1) * 16;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) total += (row[(j + (tid >> 1)) & 31] >> sh) & 0xffffu; // skewed: conflict-free
+        for (; v < nvec; v += SEGHIST_THREADS) {
+            const uint4 a = ld_stream(vbase + v);
+            if (sizeof(KeyT) == 4) {
+                count_key((KeyT) a.x); count_key((KeyT) a.y); count_key((KeyT) a.z); count_key((KeyT) a.w);
+            } else {
+                count_key((KeyT) (((uint64_t) a.y << 32) | a.x)); count_key((KeyT) (((uint64_t) a.w << 32) | a.z));
+            }
         }
-        __syncthreads();
+        const uint64_t tail0 = head + nvec * VEC;
+        if (tail0 + tid < cnt_keys) count_key(base[tail0 + tid]);
     }
-    if (tid < RADIX) hist[(size_t) blockIdx.x * RADIX + tid] = total;
+    __syncthreads();
+    if (tid < RADIX) {
+        const uint32_t *row = &cnt[tid * 32];
+        uint32_t total = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) total += row[(j + tid) & 31]; // skewed: conflict-free
+        hist[(size_t) blockIdx.x * RADIX + tid] = total;
+    }
 }
 
 // =====================================================================================
