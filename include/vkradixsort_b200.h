@@ -130,6 +130,21 @@ int vkrs_single_sort(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1,
  * the user).  histograms may be NULL. */
 int vkrs_sort_auto(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t num_elements, void *stream);
 
+/* ---- multi-GPU bucket exchange, device side (no reference counterpart: the reference is single
+ * device; BASELINE.json config 5 defines the extension).  One process per GPU runs
+ *   vkrs_key_range  -> all-reduce min/max -> pick (key_base, shift) so that
+ *                      bucket(key) = min(255, (key - key_base) >> shift) spreads the occupied key
+ *                      range over 256 order-preserving buckets;
+ *   vkrs_partition  -> keys_out = keys_in stably grouped by bucket, bucket_counts[256] (device) = the
+ *                      group sizes; contiguous bucket ranges are then dealt to the ranks, exchanged
+ *                      (all-to-all-v over NVLink) and sorted locally with vkrs_multi_sort.
+ * The host-side orchestration is vkradixsort_b200/dist.py. */
+int vkrs_key_range(vkrs_handle handle, const uint32_t *keys, uint32_t num_elements, uint32_t *min_max_out /* device, 2 x uint32 */,
+                   void *stream);
+int vkrs_partition(vkrs_handle handle, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *values_in,
+                   uint32_t *values_out, uint32_t num_elements, uint32_t key_base, uint32_t shift,
+                   uint32_t *bucket_counts /* device, 256 x uint32 */, void *stream);
+
 /* ---- host-buffer convenience = prepareBuffers + execute loop + verify's download
  * (MultiRadixSort.cpp:83-102): H2D of host_keys (pinned or pageable), sort on the device in
  * handle-owned buffers, D2H back into host_keys; returns after the data is back. */

@@ -312,3 +312,65 @@ def test_full_size_1e8_properties(handle, dev, oracle):
     expect = np.sort(keys_host)
     out = to_host(b0)
     assert oracle.test_sort(expect, out) == -1
+
+
+def test_key_range_and_partition(handle, dev, oracle):
+    """Device side of the multi-GPU exchange: bucket(key) = min(255, (key - base) >> shift), stable."""
+    from vkradixsort_b200 import dist as D
+
+    for n, mx in ((1, 0xFFFFFFFF), (1000, 0xFFFFFFFF), (300_001, 0x0FFFFFFF), (1_000_003, 0xFFFFFFFF), (50_000, 1000)):
+        keys = oracle.generate_random(n, 4000 + n, mx)
+        vals = np.arange(n, dtype=np.uint32)
+        d_k, d_v = to_dev(keys, dev), to_dev(vals, dev)
+        mm = torch.zeros(2, dtype=torch.int32, device=dev)
+        handle.key_range(d_k, n, mm)
+        lo, hi = (int(x) & 0xFFFFFFFF for x in mm.tolist())
+        assert (lo, hi) == (int(keys.min()), int(keys.max()))
+        base, shift = D.choose_bucket_map(lo, hi)
+        bucket = np.minimum(255, (keys - np.uint32(base)) >> np.uint32(shift))
+        order = np.argsort(bucket, kind="stable")
+        counts = torch.zeros(256, dtype=torch.int32, device=dev)
+        for with_vals in (False, True):
+            o_k, o_v = scratch_like(d_k), scratch_like(d_v)
+            handle.partition(d_k, o_k, n, base, shift, counts, d_v if with_vals else None, o_v if with_vals else None)
+            assert np.array_equal(to_host(o_k), keys[order]), (n, mx, with_vals)
+            assert np.array_equal(to_host(counts), np.bincount(bucket, minlength=256).astype(np.uint32))
+            if with_vals:
+                assert np.array_equal(to_host(o_v), vals[order])
+
+
+def test_example_programs(built_lib):
+    """The two example executables are the reference's own end-to-end tests: same
+    stdout lines, exit code 0 and "Test passed." on success."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bindir = os.path.join(root, "vkradixsort_b200", "bin")
+    if not os.path.exists(os.path.join(bindir, "multiradixsortexample")):
+        subprocess.run(["make", "-C", os.path.join(root, "examples"), "-s"], check=True)
+    for args in (["multiradixsortexample"], ["multiradixsortexample", "100003", "3", "--seed", "7", "--bits", "32"],
+                 ["multiradixsortexample", "1e7", "32", "--fast", "--seed", "9"], ["singleradixsortexample", "1000", "--seed", "1"],
+                 ["singleradixsortexample"]):
+        r = subprocess.run([os.path.join(bindir, args[0])] + args[1:], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        tag = "[MultiRadixSort] " if args[0].startswith("multi") else "[SingleRadixSort] "
+        lines = r.stdout.strip().splitlines()
+        assert lines[0].startswith(tag + "Sorting ") and lines[0].endswith("32bit numbers.")
+        assert any(l.startswith(tag + "GPU sort finished in ") and l.endswith("[ms].") for l in lines)
+        assert any(l.startswith(tag + "CPU sort finished in ") for l in lines)
+        assert lines[-1] == tag + "Test passed."
+
+
+def test_two_gpu_bucket_exchange():
+    """BASELINE.json config 5 in miniature: 2 ranks over NCCL, checked against numpy on rank 0."""
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541",
+                        os.path.join(root, "tests", "dist_gpu_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DIST_OK" in r.stdout

@@ -28,7 +28,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_global_invocation_size", "vkrs_workgroup_count",
     "vkrs_multi_histograms", "vkrs_multi_scatter", "vkrs_multi_pass",
     "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
-    "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host",
+    "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host", "vkrs_key_range", "vkrs_partition",
     "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
     "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
@@ -92,6 +92,8 @@ def load() -> ctypes.CDLL:
         "vkrs_single_sort": (i32, [vp, vp, vp, spc, vp]),
         "vkrs_sort_auto": (i32, [vp, vp, vp, u32, vp]),
         "vkrs_multi_sort_host": (i32, [vp, vp, u32, vp]),
+        "vkrs_key_range": (i32, [vp, vp, u32, vp, vp]),
+        "vkrs_partition": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, vp, vp]),
         "vkrs_check_device_error": (i32, [vp, vp]),
         "vkrs_num_variants": (i32, []),
         "vkrs_variant_name": (ctypes.c_char_p, [i32]),
@@ -230,6 +232,15 @@ class Handle:
 
     def multi_sort_host(self, host_keys, num_elements: int, stream=None):
         self._check(self._lib.vkrs_multi_sort_host(self._h, _ptr(host_keys), num_elements, _stream(stream)))
+
+    # ---- multi-GPU partition step ----
+    def key_range(self, keys, num_elements: int, min_max_out, stream=None):
+        self._check(self._lib.vkrs_key_range(self._h, _ptr(keys), num_elements, _ptr(min_max_out), _stream(stream)))
+
+    def partition(self, keys_in, keys_out, num_elements: int, key_base: int, shift: int, bucket_counts,
+                  values_in=None, values_out=None, stream=None):
+        self._check(self._lib.vkrs_partition(self._h, _ptr(keys_in), _ptr(keys_out), _ptr(values_in), _ptr(values_out),
+                                             num_elements, key_base, shift, _ptr(bucket_counts), _stream(stream)))
 
     # ---- misc ----
     def check_device_error(self, stream=None):

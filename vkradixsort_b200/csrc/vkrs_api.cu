@@ -241,12 +241,12 @@ int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
 }
 
 // One digit pass of the segmented path: count (one CTA per segment), then the persistent scatter.
-template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS>
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false>
 int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
-                 uint32_t shift, cudaStream_t stream) {
+                 uint32_t shift, cudaStream_t stream, uint32_t key_base = 0, uint32_t *bucket_totals = nullptr) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     constexpr uint32_t TILE = Smem::Group::TILE;
-    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS>;
+    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION>;
     static thread_local int configured_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (configured_device != h->device) {
@@ -266,12 +266,16 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     if (r) return r;
     {
         LaunchScope scope(h, "segment_histogram_kernel", stream);
-        segment_histogram_kernel<KeyT><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, TILE, tiles, h->seg_hist);
+        segment_histogram_kernel<KeyT, PARTITION><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, key_base, TILE, tiles, h->seg_hist);
     }
     {
         LaunchScope scope(h, HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
-        kernel<<<ctas, GROUPS * WORKERS + 32, sizeof(Smem), stream>>>(in, out, vin, vout, n, shift, h->seg_hist, tiles,
-                                                                      h->debug_counters);
+        kernel<<<ctas, GROUPS * WORKERS + 32, sizeof(Smem), stream>>>(in, out, vin, vout, n, shift, key_base, h->seg_hist,
+                                                                      tiles, h->debug_counters);
+    }
+    if (bucket_totals) {
+        LaunchScope scope(h, "segment_column_sum_kernel", stream);
+        segment_column_sum_kernel<<<1, RADIX, 0, stream>>>(h->seg_hist, segments, bucket_totals);
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
@@ -708,6 +712,44 @@ int vkrs_multi_sort_u64(vkrs_handle h, uint64_t *buf0, uint64_t *buf1, uint32_t 
         if (r) return r;
     }
     return VKRS_OK;
+}
+
+int vkrs_key_range(vkrs_handle h, const uint32_t *keys, uint32_t num_elements, uint32_t *min_max_out, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!min_max_out || (!keys && num_elements > 0)) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t init[2] = {0xFFFFFFFFu, 0u};
+    VKRS_CUDA(h, cudaMemcpyAsync(min_max_out, init, sizeof init, cudaMemcpyHostToDevice, s));
+    if (num_elements > 0) {
+        LaunchScope scope(h, "key_range_kernel", s);
+        key_range_kernel<<<h->sm_count * 4, 512, 0, s>>>(keys, num_elements, min_max_out);
+    }
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int vkrs_partition(vkrs_handle h, const uint32_t *keys_in, uint32_t *keys_out, const uint32_t *values_in,
+                   uint32_t *values_out, uint32_t num_elements, uint32_t key_base, uint32_t shift,
+                   uint32_t *bucket_counts, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (num_elements >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "at most 2^30-1 keys per call");
+    if (shift > 31) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "shift=%u out of range", shift);
+    if (!bucket_counts) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "bucket_counts is NULL");
+    if ((values_in == nullptr) != (values_out == nullptr))
+        return fail(h, VKRS_ERR_INVALID_ARGUMENT, "values_in and values_out must both be given or both be NULL");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (num_elements == 0) {
+        VKRS_CUDA(h, cudaMemsetAsync(bucket_counts, 0, RADIX * sizeof(uint32_t), s));
+        return VKRS_OK;
+    }
+    if (!keys_in || !keys_out) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (values_in)
+        return launch_seg_t<uint32_t, true, PAIR_WORKERS, PAIR_KPT, 2, 1, true>(h, keys_in, keys_out, values_in, values_out,
+                                                                                num_elements, shift, s, key_base, bucket_counts);
+    return launch_seg_t<uint32_t, false, 384, 16, 2, 1, true>(h, keys_in, keys_out, nullptr, nullptr, num_elements, shift, s,
+                                                              key_base, bucket_counts);
 }
 
 int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_single_push_constants *pc,

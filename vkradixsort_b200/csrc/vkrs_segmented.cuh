@@ -26,6 +26,32 @@
 
 namespace vkrs {
 
+// Which 8-bit "digit" a pass distributes by.
+//   PARTITION == false : byte (shift/8) of the key, the reference's (key >> g_shift) & 255
+//                        (multi_radixsort.comp:100); one PRMT.
+//   PARTITION == true  : min(255, (key - base) >> shift) for an arbitrary shift -- the bucket index
+//                        of the multi-GPU exchange (vkrs_partition): an order-preserving map of the
+//                        occupied key range onto 256 buckets.  32-bit keys only.
+template <typename KeyT, bool PARTITION>
+struct DigitOf {
+    uint32_t shift, base, dsel;
+    __device__ __forceinline__ DigitOf(uint32_t shift_, uint32_t base_) : shift(shift_), base(base_), dsel(digit_selector(shift_)) {}
+    // digit of the key
+    __device__ __forceinline__ uint32_t operator()(KeyT key) const {
+        if (PARTITION) {
+            const uint32_t f = ((uint32_t) key - base) >> shift;
+            return f < 255u ? f : 255u;
+        }
+        return digit_prmt(sizeof(KeyT) == 8 ? (uint32_t) ((uint64_t) key >> (shift & 32u)) : (uint32_t) key, dsel);
+    }
+    // the word the ballots test (bit masks from bit_masks()) for a key whose digit is d
+    __device__ __forceinline__ uint32_t match_word(KeyT key, uint32_t d) const {
+        if (PARTITION) return d;
+        return sizeof(KeyT) == 8 ? (uint32_t) ((uint64_t) key >> (shift & 32u)) : (uint32_t) key;
+    }
+    __device__ __forceinline__ DigitBitMasks bit_masks() const { return DigitBitMasks(PARTITION ? 0u : (shift & 31u)); }
+};
+
 // Tiles [first, first + count) of segment g when `num_tiles` tiles are dealt to `num_segments`
 // segments as evenly as possible (host and device agree through this one function).
 __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_segments, uint32_t num_tiles,
@@ -42,10 +68,10 @@ __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_
 // =====================================================================================
 constexpr int SEGHIST_THREADS = 512;
 
-template <typename KeyT>
+template <typename KeyT, bool PARTITION>
 __global__ void __launch_bounds__(SEGHIST_THREADS)
-segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t tile_keys,
-                         uint32_t num_tiles, uint32_t *__restrict__ hist) {
+segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t key_base,
+                         uint32_t tile_keys, uint32_t num_tiles, uint32_t *__restrict__ hist) {
     __shared__ uint32_t cnt[RADIX * 32]; // [digit][lane]: bank == lane, one wavefront per atomic
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t first, count;
@@ -53,12 +79,9 @@ segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shi
     const uint64_t lo = (uint64_t) first * tile_keys;
     uint64_t hi = lo + (uint64_t) count * tile_keys;
     if (hi > n) hi = n;
-    const uint32_t wshift = sizeof(KeyT) == 8 ? (shift & 32u) : 0u;
-    const uint32_t dsel = digit_selector(shift);
+    const DigitOf<KeyT, PARTITION> digit(shift, key_base);
     uint32_t *my_col = cnt + lane;
-    auto count_key = [&](KeyT k) {
-        atomicAdd(my_col + digit_prmt((uint32_t) ((uint64_t) k >> wshift), dsel) * 32, 1u);
-    };
+    auto count_key = [&](KeyT k) { atomicAdd(my_col + digit(k) * 32, 1u); };
     for (int i = tid; i < RADIX * 32; i += SEGHIST_THREADS) cnt[i] = 0;
     __syncthreads();
     if (lo < hi) {
@@ -129,11 +152,11 @@ struct SegSmem {
     Group g[GROUPS];
 };
 
-template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS>
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false>
 __global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
 segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                          const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
-                         uint32_t shift, const uint32_t *__restrict__ hist, uint32_t num_tiles,
+                         uint32_t shift, uint32_t key_base, const uint32_t *__restrict__ hist, uint32_t num_tiles,
                          unsigned long long *dbg) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     using Group = typename Smem::Group;
@@ -205,12 +228,9 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
     segment_tiles(seg, num_segments, num_tiles, first_tile, tile_count);
     const uint32_t bar_w = 1 + grp, bar_d = 1 + GROUPS + grp; // this group's worker / digit named barriers
     const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
-    const DigitBitMasks bm(sizeof(KeyT) == 8 ? (shift & 31u) : shift);
+    const DigitOf<KeyT, PARTITION> digit(shift, key_base);
+    const DigitBitMasks bm = digit.bit_masks();
     const LaneNibbleConsts lc(lane);
-    const uint32_t dsel = digit_selector(shift);
-    auto key_word = [&](KeyT key) -> uint32_t { // the 32-bit word of the key that holds the digit
-        return sizeof(KeyT) == 8 ? (uint32_t) ((uint64_t) key >> (shift & 32u)) : (uint32_t) key;
-    };
     uint32_t *my_cnt = s.warp_cnt[warp];
     const uint32_t chunk0 = warp * (KPT * 32) + lane; // warp-striped: lane l holds chunk[i*32 + l]
 
@@ -262,7 +282,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
         for (int jj = 0; jj < KPT; ++jj) {
             const uint32_t p = gtid + jj * WORKERS;
             const KeyT k = s.sorted[p];
-            const uint32_t g = s.bin_dst[pslot][digit_prmt(key_word(k), dsel)] + p;
+            const uint32_t g = s.bin_dst[pslot][digit(k)] + p;
             if (full || p < valid) {
                 keys_out[g] = k;
                 if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
@@ -298,15 +318,15 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
         uint32_t rank2[KPT / 2];
         // Software-pipelined: the ballots of round i+1 are issued before the counter update of
         // round i, so the shared-memory round trip of one round hides behind the votes of the next.
-        uint32_t d_cur = digit_prmt(key_word(tin[chunk0]), dsel);
-        uint32_t peers_cur = match_key_table(key_word(tin[chunk0]), d_cur, bm, lc);
+        uint32_t d_cur = digit(tin[chunk0]);
+        uint32_t peers_cur = match_key_table(digit.match_word(tin[chunk0], d_cur), d_cur, bm, lc);
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             uint32_t d_next = 0, peers_next = 0;
             if (i + 1 < KPT) {
-                const uint32_t word = key_word(tin[chunk0 + (i + 1) * 32]);
-                d_next = digit_prmt(word, dsel);
-                peers_next = match_key_table(word, d_next, bm, lc);
+                const KeyT key = tin[chunk0 + (i + 1) * 32];
+                d_next = digit(key);
+                peers_next = match_key_table(digit.match_word(key, d_next), d_next, bm, lc);
             }
             const uint32_t r = my_cnt[d_cur] + __popc(peers_cur & lt_mask);
             if ((peers_cur & gt_mask) == 0) my_cnt[d_cur] = r + 1; // highest lane of the group
@@ -360,7 +380,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
 #pragma unroll
             for (int i = 0; i < SB; ++i) kb[i] = tin[chunk0 + (i0 + i) * 32];
 #pragma unroll
-            for (int i = 0; i < SB; ++i) rb[i] = my_cnt[digit_prmt(key_word(kb[i]), dsel)];
+            for (int i = 0; i < SB; ++i) rb[i] = my_cnt[digit(kb[i])];
 #pragma unroll
             for (int i = 0; i < SB; ++i) {
                 const int k = i0 + i;
@@ -390,6 +410,35 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
     if (tile_count > 0) { // drain: the last tile of the segment
         named_bar_sync(bar_w, WORKERS);
         write_out((tile_count - 1) & 1, prev_valid);
+    }
+}
+
+// =====================================================================================
+// Helpers of the multi-GPU partition step.
+// =====================================================================================
+// totals[d] = sum over the segments of hist[g][d] (the 256 bucket counts of vkrs_partition).
+__global__ void __launch_bounds__(RADIX)
+segment_column_sum_kernel(const uint32_t *__restrict__ hist, uint32_t num_segments, uint32_t *__restrict__ totals) {
+    uint32_t sum = 0;
+    for (uint32_t g = 0; g < num_segments; ++g) sum += hist[(size_t) g * RADIX + threadIdx.x];
+    totals[threadIdx.x] = sum;
+}
+
+// out[0] = min key, out[1] = max key (out pre-set to {0xFFFFFFFF, 0}); one coalesced read.
+__global__ void __launch_bounds__(512)
+key_range_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *out) {
+    uint32_t lo = 0xFFFFFFFFu, hi = 0u;
+    const uint64_t stride = (uint64_t) gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t k = ld_stream(keys + i);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    hi = __reduce_max_sync(0xffffffffu, hi);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
     }
 }
 
