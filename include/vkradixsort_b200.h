@@ -145,6 +145,23 @@ int vkrs_partition(vkrs_handle handle, const uint32_t *keys_in, uint32_t *keys_o
                    uint32_t *values_out, uint32_t num_elements, uint32_t key_base, uint32_t shift,
                    uint32_t *bucket_counts /* device, 256 x uint32 */, void *stream);
 
+/* The same partition with the exchange FUSED into it (one kernel computes the buckets and stores
+ * them straight into the owning ranks' receive buffers over NVLink peer mappings; no all-to-all):
+ *   vkrs_ipc_alloc / vkrs_ipc_open     receive buffers shared between the ranks of one node (CUDA IPC)
+ *   vkrs_partition_count               bucket counts only (the exchange plan is made from them)
+ *   vkrs_partition_scatter_p2p         must follow vkrs_partition_count on the same input and handle.
+ *                                      dst_tables (device, 512 x uint64): [b] = address where this rank's
+ *                                      keys of bucket b start in the owner's buffer, [256 + b] the same
+ *                                      for payloads (ignored without values). */
+int vkrs_ipc_alloc(vkrs_handle handle, uint64_t bytes, void **device_ptr, unsigned char *ipc_handle_64);
+int vkrs_ipc_open(vkrs_handle handle, const unsigned char *ipc_handle_64, void **device_ptr);
+int vkrs_ipc_close(vkrs_handle handle, void *device_ptr);
+int vkrs_ipc_free(vkrs_handle handle, void *device_ptr);
+int vkrs_partition_count(vkrs_handle handle, const uint32_t *keys_in, uint32_t num_elements, uint32_t key_base,
+                         uint32_t shift, int with_values, uint32_t *bucket_counts /* device, 256 x uint32 */, void *stream);
+int vkrs_partition_scatter_p2p(vkrs_handle handle, const uint32_t *keys_in, const uint32_t *values_in, uint32_t num_elements,
+                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables, void *stream);
+
 /* ---- host-buffer convenience = prepareBuffers + execute loop + verify's download
  * (MultiRadixSort.cpp:83-102): H2D of host_keys (pinned or pageable), sort on the device in
  * handle-owned buffers, D2H back into host_keys; returns after the data is back. */

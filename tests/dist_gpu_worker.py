@@ -22,8 +22,8 @@ def main():
         rng = np.random.default_rng(17 + rank)
         keys = rng.integers(0, hi, size=n, dtype=np.uint64).astype(np.uint32)
         vals = (np.arange(n, dtype=np.uint32) + np.uint32(rank * n))
-        for pairs in (False, True):
-            sorter = DistributedSorter(h, n, world, rank, dev, pairs=pairs)
+        for pairs, p2p in ((False, False), (True, False), (False, True), (True, True)):
+            sorter = DistributedSorter(h, n, world, rank, dev, pairs=pairs, p2p=p2p)
             k = torch.from_numpy(keys.view(np.int32).copy()).to(dev)
             v = torch.from_numpy(vals.view(np.int32).copy()).to(dev)
             if pairs:
@@ -31,6 +31,7 @@ def main():
             else:
                 out_k, out_v = sorter.sort(k, torch.empty_like(k)), None
             h.check_device_error()
+            assert sorter.used_p2p == p2p, (case, pairs, p2p)
             # gather everything on rank 0 and compare with numpy's stable sort of the concatenation
             sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
             dist.all_gather(sizes, torch.tensor([out_k.numel()], dtype=torch.int64, device=dev))
@@ -51,11 +52,12 @@ def main():
 
             got_k, all_k = gather(out_k), gather_in(keys)
             order = np.argsort(all_k, kind="stable")
-            assert np.array_equal(got_k, all_k[order]), (case, pairs)
+            assert np.array_equal(got_k, all_k[order]), (case, pairs, p2p)
             if pairs:
                 assert np.array_equal(gather(out_v), gather_in(vals)[order]), (case, "values")
             if case != "dups":
                 assert max(sizes) / (sum(sizes) / world) < 1.05, sizes
+            sorter.close()
     h.close()
     dist.barrier()
     if rank == 0:

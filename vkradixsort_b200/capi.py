@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_multi_histograms", "vkrs_multi_scatter", "vkrs_multi_pass",
     "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
     "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host", "vkrs_key_range", "vkrs_partition",
+    "vkrs_partition_count", "vkrs_partition_scatter_p2p", "vkrs_ipc_alloc", "vkrs_ipc_open", "vkrs_ipc_close", "vkrs_ipc_free",
     "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
     "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
@@ -94,6 +95,12 @@ def load() -> ctypes.CDLL:
         "vkrs_multi_sort_host": (i32, [vp, vp, u32, vp]),
         "vkrs_key_range": (i32, [vp, vp, u32, vp, vp]),
         "vkrs_partition": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, vp, vp]),
+        "vkrs_partition_count": (i32, [vp, vp, u32, u32, u32, i32, vp, vp]),
+        "vkrs_partition_scatter_p2p": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
+        "vkrs_ipc_alloc": (i32, [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]),
+        "vkrs_ipc_open": (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
+        "vkrs_ipc_close": (i32, [vp, vp]),
+        "vkrs_ipc_free": (i32, [vp, vp]),
         "vkrs_check_device_error": (i32, [vp, vp]),
         "vkrs_num_variants": (i32, []),
         "vkrs_variant_name": (ctypes.c_char_p, [i32]),
@@ -241,6 +248,34 @@ class Handle:
                   values_in=None, values_out=None, stream=None):
         self._check(self._lib.vkrs_partition(self._h, _ptr(keys_in), _ptr(keys_out), _ptr(values_in), _ptr(values_out),
                                              num_elements, key_base, shift, _ptr(bucket_counts), _stream(stream)))
+
+    def partition_count(self, keys_in, num_elements: int, key_base: int, shift: int, bucket_counts, with_values=False,
+                        stream=None):
+        self._check(self._lib.vkrs_partition_count(self._h, _ptr(keys_in), num_elements, key_base, shift,
+                                                   1 if with_values else 0, _ptr(bucket_counts), _stream(stream)))
+
+    def partition_scatter_p2p(self, keys_in, num_elements: int, key_base: int, shift: int, dst_tables, values_in=None,
+                              stream=None):
+        self._check(self._lib.vkrs_partition_scatter_p2p(self._h, _ptr(keys_in), _ptr(values_in), num_elements, key_base,
+                                                         shift, _ptr(dst_tables), _stream(stream)))
+
+    def ipc_alloc(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle) of a cudaMalloc'ed buffer other ranks can map."""
+        ptr = ctypes.c_void_p()
+        hd = ctypes.create_string_buffer(64)
+        self._check(self._lib.vkrs_ipc_alloc(self._h, nbytes, ctypes.byref(ptr), hd))
+        return int(ptr.value), hd.raw
+
+    def ipc_open(self, ipc_handle: bytes) -> int:
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.vkrs_ipc_open(self._h, ipc_handle, ctypes.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, ptr: int):
+        self._check(self._lib.vkrs_ipc_close(self._h, ptr))
+
+    def ipc_free(self, ptr: int):
+        self._check(self._lib.vkrs_ipc_free(self._h, ptr))
 
     # ---- misc ----
     def check_device_error(self, stream=None):

@@ -241,12 +241,15 @@ int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
 }
 
 // One digit pass of the segmented path: count (one CTA per segment), then the persistent scatter.
-template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false>
+// do_count / do_scatter let the multi-GPU path run the two halves separately (the exchange plan is
+// made from the counts in between); dst_tables != nullptr selects the peer-to-peer write-out.
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false, bool P2P = false>
 int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
-                 uint32_t shift, cudaStream_t stream, uint32_t key_base = 0, uint32_t *bucket_totals = nullptr) {
+                 uint32_t shift, cudaStream_t stream, uint32_t key_base = 0, uint32_t *bucket_totals = nullptr,
+                 bool do_count = true, bool do_scatter = true, const unsigned long long *dst_tables = nullptr) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     constexpr uint32_t TILE = Smem::Group::TILE;
-    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION>;
+    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION, P2P>;
     static thread_local int configured_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (configured_device != h->device) {
@@ -264,18 +267,20 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     const uint32_t segments = ctas * GROUPS;
     int r = grow(h, h->seg_hist, h->seg_hist_rows, (uint64_t) segments, RADIX * sizeof(uint32_t), false);
     if (r) return r;
-    {
-        LaunchScope scope(h, "segment_histogram_kernel", stream);
-        segment_histogram_kernel<KeyT, PARTITION><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, key_base, TILE, tiles, h->seg_hist);
+    if (do_count) {
+        {
+            LaunchScope scope(h, "segment_histogram_kernel", stream);
+            segment_histogram_kernel<KeyT, PARTITION><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, key_base, TILE, tiles, h->seg_hist);
+        }
+        if (bucket_totals) {
+            LaunchScope scope(h, "segment_column_sum_kernel", stream);
+            segment_column_sum_kernel<<<1, RADIX, 0, stream>>>(h->seg_hist, segments, bucket_totals);
+        }
     }
-    {
-        LaunchScope scope(h, HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
+    if (do_scatter) {
+        LaunchScope scope(h, P2P ? "segmented_scatter_kernel<p2p>" : HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
         kernel<<<ctas, GROUPS * WORKERS + 32, sizeof(Smem), stream>>>(in, out, vin, vout, n, shift, key_base, h->seg_hist,
-                                                                      tiles, h->debug_counters);
-    }
-    if (bucket_totals) {
-        LaunchScope scope(h, "segment_column_sum_kernel", stream);
-        segment_column_sum_kernel<<<1, RADIX, 0, stream>>>(h->seg_hist, segments, bucket_totals);
+                                                                      tiles, h->debug_counters, dst_tables);
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
@@ -750,6 +755,84 @@ int vkrs_partition(vkrs_handle h, const uint32_t *keys_in, uint32_t *keys_out, c
                                                                                 num_elements, shift, s, key_base, bucket_counts);
     return launch_seg_t<uint32_t, false, 384, 16, 2, 1, true>(h, keys_in, keys_out, nullptr, nullptr, num_elements, shift, s,
                                                               key_base, bucket_counts);
+}
+
+int vkrs_partition_count(vkrs_handle h, const uint32_t *keys_in, uint32_t num_elements, uint32_t key_base, uint32_t shift,
+                         int with_values, uint32_t *bucket_counts, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (num_elements >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "at most 2^30-1 keys per call");
+    if (shift > 31) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "shift=%u out of range", shift);
+    if (!bucket_counts) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "bucket_counts is NULL");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (num_elements == 0) {
+        VKRS_CUDA(h, cudaMemsetAsync(bucket_counts, 0, RADIX * sizeof(uint32_t), s));
+        return VKRS_OK;
+    }
+    if (!keys_in) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (with_values)
+        return launch_seg_t<uint32_t, true, PAIR_WORKERS, PAIR_KPT, 2, 1, true, true>(h, keys_in, nullptr, nullptr, nullptr, num_elements,
+                                                                                      shift, s, key_base, bucket_counts, true, false);
+    return launch_seg_t<uint32_t, false, 384, 16, 2, 1, true, true>(h, keys_in, nullptr, nullptr, nullptr, num_elements, shift, s,
+                                                                    key_base, bucket_counts, true, false);
+}
+
+int vkrs_partition_scatter_p2p(vkrs_handle h, const uint32_t *keys_in, const uint32_t *values_in, uint32_t num_elements,
+                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (num_elements == 0) return VKRS_OK;
+    if (num_elements >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "at most 2^30-1 keys per call");
+    if (!keys_in || !dst_tables) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const unsigned long long *tables = reinterpret_cast<const unsigned long long *>(dst_tables);
+    if (values_in)
+        return launch_seg_t<uint32_t, true, PAIR_WORKERS, PAIR_KPT, 2, 1, true, true>(h, keys_in, nullptr, values_in, nullptr, num_elements,
+                                                                                      shift, s, key_base, nullptr, false, true, tables);
+    return launch_seg_t<uint32_t, false, 384, 16, 2, 1, true, true>(h, keys_in, nullptr, nullptr, nullptr, num_elements, shift, s,
+                                                                    key_base, nullptr, false, true, tables);
+}
+
+int vkrs_ipc_alloc(vkrs_handle h, uint64_t bytes, void **device_ptr, unsigned char *ipc_handle_64) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!device_ptr || !ipc_handle_64) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL output");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    DeviceGuard guard(h->device);
+    void *p = nullptr;
+    VKRS_CUDA(h, cudaMalloc(&p, bytes ? bytes : 256));
+    cudaIpcMemHandle_t hd;
+    cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(h, VKRS_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(ipc_handle_64, &hd, 64);
+    *device_ptr = p;
+    return VKRS_OK;
+}
+
+int vkrs_ipc_open(vkrs_handle h, const unsigned char *ipc_handle_64, void **device_ptr) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!device_ptr || !ipc_handle_64) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL argument");
+    DeviceGuard guard(h->device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, ipc_handle_64, 64);
+    VKRS_CUDA(h, cudaIpcOpenMemHandle(device_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return VKRS_OK;
+}
+
+int vkrs_ipc_close(vkrs_handle h, void *device_ptr) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    VKRS_CUDA(h, cudaIpcCloseMemHandle(device_ptr));
+    return VKRS_OK;
+}
+
+int vkrs_ipc_free(vkrs_handle h, void *device_ptr) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(h->device);
+    VKRS_CUDA(h, cudaFree(device_ptr));
+    return VKRS_OK;
 }
 
 int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_single_push_constants *pc,

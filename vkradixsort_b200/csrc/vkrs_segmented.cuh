@@ -144,6 +144,7 @@ struct SegGroupSmem {
     uint32_t bin_dst[2][RADIX];                          // global start of the digit run minus its start in the tile
     uint32_t scan_scratch[8];
     alignas(8) uint64_t full[2], empty[2];
+    alignas(8) unsigned long long dst_ptr[2][RADIX];     // P2P mode: per-bucket destination arrays (keys, payloads)
 };
 
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS>
@@ -152,12 +153,19 @@ struct SegSmem {
     Group g[GROUPS];
 };
 
-template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false>
+// P2P == true (multi-GPU exchange fused into the partition): there is no single output array.
+// dst_tables[b] / dst_tables[256 + b] hold, for bucket b, the address where THIS rank's keys /
+// payloads of that bucket start inside the receive buffer of the rank that owns the bucket -- a
+// peer GPU's memory mapped over NVLink (or this GPU's own).  The tile is ranked and staged exactly as
+// in the local case; only the write-out addresses differ, so the exchange costs no extra pass: the
+// stores go straight over NVLink while other tiles are being ranked.
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false,
+          bool P2P = false>
 __global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
 segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                          const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
                          uint32_t shift, uint32_t key_base, const uint32_t *__restrict__ hist, uint32_t num_tiles,
-                         unsigned long long *dbg) {
+                         unsigned long long *dbg, const unsigned long long *__restrict__ dst_tables) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     using Group = typename Smem::Group;
     constexpr int WARPS = Group::WARPS;
@@ -261,7 +269,12 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
 #pragma unroll
         for (int w = 0; w < RADIX / 32; ++w)
             if (w < warp) warp_prefix += s.scan_scratch[w];
-        running_base = warp_prefix + incl - total + below;
+        // local output: digits are laid out one after the other; P2P: every bucket has its own array
+        running_base = P2P ? below : warp_prefix + incl - total + below;
+        if (P2P) {
+            s.dst_ptr[0][gtid] = dst_tables[gtid];
+            if (HAS_VALUES) s.dst_ptr[1][gtid] = dst_tables[RADIX + gtid];
+        }
         named_bar_sync(bar_d, RADIX); // scan_scratch is reused by the per-tile scan
     }
 
@@ -282,10 +295,16 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
         for (int jj = 0; jj < KPT; ++jj) {
             const uint32_t p = gtid + jj * WORKERS;
             const KeyT k = s.sorted[p];
-            const uint32_t g = s.bin_dst[pslot][digit(k)] + p;
+            const uint32_t d = digit(k);
+            const uint32_t g = s.bin_dst[pslot][d] + p;
             if (full || p < valid) {
-                keys_out[g] = k;
-                if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
+                if (P2P) {
+                    reinterpret_cast<KeyT *>(s.dst_ptr[0][d])[g] = k;
+                    if (HAS_VALUES) reinterpret_cast<uint32_t *>(s.dst_ptr[1][d])[g] = s.sorted_v[p];
+                } else {
+                    keys_out[g] = k;
+                    if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
+                }
             }
         }
     };

@@ -9,8 +9,13 @@ N GPUs hold n keys each, the result is globally sorted with rank r holding the r
     3. plan           all-gather of the counts; contiguous bucket ranges are dealt to the ranks so
                       that the loads are as even as the bucket granularity allows (pure host
                       arithmetic: plan_exchange)
-    4. exchange       ONE all-to-all-v (torch.distributed.all_to_all_single; NCCL over NVLink /
-                      NVSwitch on GPUs): the slices are already contiguous, nothing is packed
+    4. exchange       fused (default on GPUs of one node): the partition kernel itself stores every
+                      bucket straight into the owning rank's receive buffer through CUDA-IPC peer
+                      mappings (vkrs_partition_count -> plan -> vkrs_partition_scatter_p2p), so the keys
+                      cross NVLink while other tiles are still being ranked and no separate collective
+                      moves data; or staged: vkrs_partition + ONE all-to-all-v (all_to_all_single; the
+                      slices are already contiguous, nothing is packed) -- the portable path, also used
+                      when a receive buffer would overflow
     5. local sort     vkrs_multi_sort of what arrived.  Stable end to end: pieces arrive in source-rank
                       order, each in original order, and the LSD sort keeps ties in place.
 
@@ -45,6 +50,24 @@ class ExchangePlan:
     send_counts: list  # keys this rank sends to each rank
     recv_counts: list  # keys this rank receives from each rank
     imbalance: float   # max load / mean load over the ranks
+
+
+def destination_offsets(all_counts: np.ndarray, boundaries: list, rank: int) -> tuple[np.ndarray, np.ndarray]:
+    """For the fused exchange: (owner[b], offset[b]) = which rank owns bucket b and at which element of
+    that rank's receive buffer THIS rank's keys of bucket b start.  The receive buffer of rank r is laid
+    out source rank by source rank, each source's part bucket by bucket -- exactly what the all-to-all-v
+    of the staged path produces, so both exchanges give bit-identical buffers."""
+    all_counts = np.asarray(all_counts, dtype=np.int64)
+    world = all_counts.shape[0]
+    owner = np.zeros(NUM_BUCKETS, dtype=np.int64)
+    offset = np.zeros(NUM_BUCKETS, dtype=np.int64)
+    for r in range(world):
+        lo, hi = boundaries[r], boundaries[r + 1]
+        owner[lo:hi] = r
+        before_me = int(all_counts[:rank, lo:hi].sum())  # parts of the lower source ranks
+        mine = all_counts[rank, lo:hi]
+        offset[lo:hi] = before_me + np.concatenate([[0], np.cumsum(mine)[:-1]]) if hi > lo else 0
+    return owner, offset
 
 
 def plan_exchange(all_counts: np.ndarray, rank: int) -> ExchangePlan:
@@ -96,6 +119,13 @@ class DeviceOps:
         self.handle.partition(keys_in, keys_out, n, key_base, shift, self.counts, values_in, values_out)
         return self.counts
 
+    def partition_count(self, keys_in, n, key_base, shift, with_values=False):
+        self.handle.partition_count(keys_in, n, key_base, shift, self.counts, with_values)
+        return self.counts
+
+    def partition_scatter_p2p(self, keys_in, n, key_base, shift, dst_tables, values_in=None):
+        self.handle.partition_scatter_p2p(keys_in, n, key_base, shift, dst_tables, values_in)
+
     def local_sort(self, buf0, buf1, n, val0=None, val1=None):
         from . import capi
 
@@ -110,30 +140,87 @@ class DeviceOps:
 
 
 class DistributedSorter:
-    """Keys are int32-typed torch tensors holding uint32 bit patterns (torch has no uint32 math)."""
+    """Keys are int32-typed torch tensors holding uint32 bit patterns (torch has no uint32 math).
+
+    p2p=None picks the fused peer-to-peer exchange when the device path is in use and world > 1."""
 
     def __init__(self, handle, n_local: int, world: int, rank: int, device, pairs: bool = False, ops=None,
-                 group=None, slack: float = 1.25):
+                 group=None, slack: float = 1.25, p2p: bool | None = None):
         import torch
         import torch.distributed as dist
 
         self.torch, self.dist = torch, dist
         self.world, self.rank, self.group = world, rank, group
+        self.handle, self.device = handle, device
         self.ops = ops if ops is not None else DeviceOps(handle, device)
         self.pairs = pairs
+        self.p2p = (ops is None and world > 1) if p2p is None else p2p
         self.capacity = int(n_local * slack) + 1024
-        self.recv = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)]
-        self.recv_vals = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)] if pairs else None
         self.last_plan: ExchangePlan | None = None
         self.exchange_bytes = 0
+        self.used_p2p = False
+        self._ipc_owned, self._ipc_opened = [], []
+        self._alloc()
+
+    # ---- buffers ----
+    def _alloc(self):
+        self.recv = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)]
+        self.recv_vals = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)] if self.pairs else None
+        if self.p2p:
+            self._alloc_p2p()
+
+    def _alloc_p2p(self):
+        """Receive buffers every rank of the node can store into: cudaMalloc + CUDA IPC, wrapped as
+        torch tensors for the local sort."""
+        torch, dist = self.torch, self.dist
+        self._release_p2p()
+        nbytes = 4 * self.capacity
+        self.peer_ptrs = []
+        for which in range(2 if self.pairs else 1):  # keys, payloads
+            ptr, hd = self.handle.ipc_alloc(nbytes)
+            self._ipc_owned.append(ptr)
+            mine = torch.frombuffer(bytearray(hd), dtype=torch.uint8).to(self.device)
+            everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(everyone, mine, group=self.group)
+            handles = everyone.cpu().numpy().tobytes()
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(ptr)
+                else:
+                    p = self.handle.ipc_open(handles[64 * r:64 * (r + 1)])
+                    self._ipc_opened.append(p)
+                    ptrs.append(p)
+            self.peer_ptrs.append(ptrs)
+            t = _tensor_from_pointer(torch, ptr, self.capacity, self.device)
+            if which == 0:
+                self.recv[0] = t
+            else:
+                self.recv_vals[0] = t
+        self.dst_tables = torch.zeros(2 * NUM_BUCKETS, dtype=torch.int64, device=self.device)
+        self._dst_host = torch.zeros(2 * NUM_BUCKETS, dtype=torch.int64).pin_memory()
+
+    def _release_p2p(self):
+        if self._ipc_opened or self._ipc_owned:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier(group=self.group)  # nobody may still be storing into a buffer that goes away
+        for p in self._ipc_opened:
+            self.handle.ipc_close(p)
+        for p in self._ipc_owned:
+            self.handle.ipc_free(p)
+        self._ipc_opened, self._ipc_owned = [], []
+
+    def close(self):
+        if self.p2p:
+            self._release_p2p()
 
     def _ensure(self, n):
         if n > self.capacity:
             self.capacity = int(n * 1.1) + 1024
-            self.recv = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)]
-            if self.pairs:
-                self.recv_vals = [self.ops.empty(self.capacity), self.ops.empty(self.capacity)]
+            self._alloc()
 
+    # ---- the sort ----
     def sort(self, keys, scratch, values=None, values_scratch=None):
         """keys/scratch: n-element device buffers of this rank (scratch is overwritten).  Returns the
         sorted keys this rank owns after the exchange (a view into an internal buffer), or
@@ -152,28 +239,59 @@ class DistributedSorter:
         kmin, neg_kmax = (int(x) for x in t.tolist())
         key_base, shift = choose_bucket_map(kmin, -neg_kmax)
 
-        # 2. stable partition by bucket
-        counts = self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
+        # 2. bucket counts (fused exchange) or the whole stable partition (staged exchange)
+        if self.p2p:
+            counts = self.ops.partition_count(keys, n, key_base, shift, values is not None)
+        else:
+            counts = self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
 
-        # 3. plan from everybody's bucket counts
+        # 3. plan from everybody's bucket counts.  The all-gather also orders this step after every
+        #    rank's previous local sort, so the receive buffers are free to be overwritten.
         gathered = torch.empty(self.world * NUM_BUCKETS, dtype=counts.dtype, device=counts.device)
         dist.all_gather_into_tensor(gathered, counts, group=self.group)
-        plan = plan_exchange(gathered.view(self.world, NUM_BUCKETS).cpu().numpy(), self.rank)
+        all_counts = gathered.view(self.world, NUM_BUCKETS).cpu().numpy()
+        plan = plan_exchange(all_counts, self.rank)
         self.last_plan = plan
         total_recv = sum(plan.recv_counts)
-        self._ensure(total_recv)
-
-        # 4. one all-to-all-v; the send slices are contiguous in `scratch`
+        self.exchange_bytes = 4 * (n - plan.send_counts[self.rank]) * (2 if values is not None else 1)
+        largest = max(int(all_counts[:, plan.boundaries[r]:plan.boundaries[r + 1]].sum()) for r in range(self.world))
+        fused = self.p2p and largest <= self.capacity  # every rank takes the same decision
+        self.used_p2p = fused
+        if not fused:
+            self._ensure(total_recv)
         recv = self.recv[0][:total_recv]
-        dist.all_to_all_single(recv, scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
-        self.exchange_bytes = 4 * (n - plan.send_counts[self.rank])
-        recv_v = None
-        if values is not None:
-            recv_v = self.recv_vals[0][:total_recv]
-            dist.all_to_all_single(recv_v, values_scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
+        recv_v = self.recv_vals[0][:total_recv] if values is not None else None
+
+        # 4. exchange
+        if fused:
+            owner, offset = destination_offsets(all_counts, plan.boundaries, self.rank)
+            tab = self._dst_host.numpy()
+            for which in range(2 if values is not None else 1):
+                base = np.array(self.peer_ptrs[which], dtype=np.int64)[owner]
+                tab[which * NUM_BUCKETS:(which + 1) * NUM_BUCKETS] = base + 4 * offset
+            self.dst_tables.copy_(self._dst_host, non_blocking=True)
+            self.ops.partition_scatter_p2p(keys, n, key_base, shift, self.dst_tables, values)
+            dist.barrier(group=self.group)  # every rank's stores have landed before anybody sorts
+        else:
+            if self.p2p:  # overflow fallback: the staged path still needs the partitioned array
+                self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
+            dist.all_to_all_single(recv, scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
+            if values is not None:
+                dist.all_to_all_single(recv_v, values_scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
 
         # 5. local sort of this rank's key range
         if total_recv > 0:
             self.ops.local_sort(recv, self.recv[1][:total_recv], total_recv,
                                 recv_v, self.recv_vals[1][:total_recv] if recv_v is not None else None)
         return (recv, recv_v) if values is not None else recv
+
+
+def _tensor_from_pointer(torch, ptr: int, numel: int, device):
+    """int32 torch tensor over `numel` elements of device memory owned elsewhere (no copy, no free)."""
+
+    class _Ext:
+        pass
+
+    ext = _Ext()
+    ext.__cuda_array_interface__ = {"shape": (numel,), "typestr": "<i4", "data": (ptr, False), "version": 3}
+    return torch.as_tensor(ext, device=device)
