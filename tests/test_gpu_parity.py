@@ -200,7 +200,7 @@ def test_single_sort_matches_oracle(dev, oracle, built_lib):
 
 
 def test_sort_auto_crossover(handle, dev, oracle):
-    for n in (1, 1000, 4096, 4097, 10_000, 100_000):
+    for n in (1, 1000, 4096, 4097, 12_288, 12_289, 100_000):
         keys = oracle.generate_random(n, 17 + n, 0xFFFFFFFF)
         b0 = to_dev(keys, dev)
         b1 = scratch_like(b0)

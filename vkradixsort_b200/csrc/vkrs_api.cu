@@ -32,8 +32,8 @@ constexpr int NUM_VARIANTS = 8;
 //   "pipe"   = onesweep_pipelined_kernel (single sweep, persistent, look-back on a control group)
 //   "simple" = onesweep_pass_kernel (single sweep, one tile per CTA)
 const PassConfig kVariants[NUM_VARIANTS] = {
-    {"seg 2x384x16", 384, 16, 1},  {"seg 2x480x16", 480, 16, 1},  {"seg 2x384x20", 384, 20, 1},
-    {"seg 3x256x20", 256, 20, 1},  {"seg 3x320x16", 320, 16, 1},  {"seg 1x512x12 2cta", 512, 12, 2},
+    {"seg 2x384x16", 384, 16, 1},  {"seg 2x416x16", 416, 16, 1},  {"seg 2x384x20", 384, 20, 1},
+    {"seg 2x352x18", 352, 18, 1},  {"seg 2x448x14", 448, 14, 1},  {"seg 1x512x12 2cta", 512, 12, 2},
     {"pipe 512x16 1cta", 512, 16, 1}, {"simple 512x16 ptx", 512, 16, 2},
 };
 constexpr int DEFAULT_VARIANT = 0;
@@ -43,7 +43,7 @@ constexpr int PAIR_WORKERS = 256, PAIR_KPT = 16; // segmented path, two worker g
 constexpr int U64_WORKERS = 256, U64_KPT = 16;
 constexpr int STAGED_THREADS = 256, STAGED_KPT = 16;
 constexpr int SINGLE_THREADS = 1024, SINGLE_KPT = 8;
-constexpr uint32_t AUTO_SINGLE_MAX = 4096; // vkrs_sort_auto: single path up to here (tuned on B200)
+constexpr uint32_t AUTO_SINGLE_MAX = 12288; // vkrs_sort_auto: single path up to here (measured crossover ~1.5e4, profiles/r01_nsweep.jsonl)
 
 thread_local std::string g_create_error;
 
@@ -290,10 +290,10 @@ int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t
                     cudaStream_t stream) {
     switch (h->variant) {
         case 0: return launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 1: return launch_seg_t<uint32_t, false, 480, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 1: return launch_seg_t<uint32_t, false, 416, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
         case 2: return launch_seg_t<uint32_t, false, 384, 20, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 3: return launch_seg_t<uint32_t, false, 256, 20, 3, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 4: return launch_seg_t<uint32_t, false, 320, 16, 3, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 3: return launch_seg_t<uint32_t, false, 352, 18, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 4: return launch_seg_t<uint32_t, false, 448, 14, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
         case 5: return launch_seg_t<uint32_t, false, 512, 12, 1, 2>(h, in, out, nullptr, nullptr, n, shift, stream);
         case 6: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
         case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);

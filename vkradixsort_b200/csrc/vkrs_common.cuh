@@ -138,7 +138,8 @@ __device__ __forceinline__ uint32_t match_key_table(uint32_t key_word, uint32_t 
     for (int b = 0; b < RADIX_BITS; ++b) B[b] = ballot_bit(key_word, bm.m[b]);
     const uint32_t lo = (B[0] ^ lc.c[0]) & (B[1] ^ lc.c[1]) & (B[2] ^ lc.c[2]) & (B[3] ^ lc.c[3]);
     const uint32_t hi = (B[4] ^ lc.c[0]) & (B[5] ^ lc.c[1]) & (B[6] ^ lc.c[2]) & (B[7] ^ lc.c[3]);
-    return __shfl_sync(0xffffffffu, lo, (int) (digit & 15u)) & __shfl_sync(0xffffffffu, hi, (int) (digit >> 4));
+    // shfl takes the source lane modulo 32 and lane i and i+16 hold the same `lo` entry: no mask needed
+    return __shfl_sync(0xffffffffu, lo, (int) digit) & __shfl_sync(0xffffffffu, hi, (int) (digit >> 4));
 }
 
 // Byte extraction of the current digit (shift is a multiple of 8): one PRMT instead of shift + mask.
