@@ -180,6 +180,23 @@ int ensure_status(vkrs_context *h, uint64_t tiles) {
     return VKRS_OK;
 }
 
+// Launch with programmatic dependent launch enabled: the grid may be scheduled while the previous
+// kernel of the stream is finishing; the kernels call grid_dependency_wait() before consuming.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <typename Kernel>
 int set_smem(vkrs_context *h, Kernel kernel, size_t bytes) {
     VKRS_CUDA(h, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
@@ -270,7 +287,8 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     if (do_count) {
         {
             LaunchScope scope(h, "segment_histogram_kernel", stream);
-            segment_histogram_kernel<KeyT, PARTITION><<<segments, SEGHIST_THREADS, 0, stream>>>(in, n, shift, key_base, TILE, tiles, h->seg_hist);
+            VKRS_CUDA(h, launch_pdl(segment_histogram_kernel<KeyT, PARTITION>, dim3(segments), dim3(SEGHIST_THREADS), 0, stream, in, n, shift,
+                                    key_base, TILE, tiles, h->seg_hist));
         }
         if (bucket_totals) {
             LaunchScope scope(h, "segment_column_sum_kernel", stream);
@@ -279,8 +297,8 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     }
     if (do_scatter) {
         LaunchScope scope(h, P2P ? "segmented_scatter_kernel<p2p>" : HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
-        kernel<<<ctas, GROUPS * WORKERS + 32, sizeof(Smem), stream>>>(in, out, vin, vout, n, shift, key_base, h->seg_hist,
-                                                                      tiles, h->debug_counters, dst_tables);
+        VKRS_CUDA(h, launch_pdl(kernel, dim3(ctas), dim3(GROUPS * WORKERS + 32), sizeof(Smem), stream, in, out, vin, vout, n, shift,
+                                key_base, (const uint32_t *) h->seg_hist, tiles, h->debug_counters, dst_tables));
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;

@@ -19,6 +19,11 @@ constexpr int LOOKBACK_WINDOW = 8;                  // earlier tiles polled toge
 
 enum DeviceError : uint32_t { DEVERR_NONE = 0, DEVERR_LOOKBACK_TIMEOUT = 1 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still draining; it must not touch the
+// predecessor's output before this returns.  A no-op for ordinary launches.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t lanemask_lt() {
     uint32_t m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

@@ -83,6 +83,7 @@ segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shi
     uint32_t *my_col = cnt + lane;
     auto count_key = [&](KeyT k) { atomicAdd(my_col + digit(k) * 32, 1u); };
     for (int i = tid; i < RADIX * 32; i += SEGHIST_THREADS) cnt[i] = 0;
+    grid_dependency_wait(); // programmatic dependent launch: everything above overlaps the previous kernel's tail
     __syncthreads();
     if (lo < hi) {
         constexpr int VEC = 16 / sizeof(KeyT);
@@ -192,6 +193,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             }
         mbar_fence_init();
     }
+    grid_dependency_wait(); // the histogram matrix and (in later passes) the keys come from earlier kernels
     __syncthreads();
 
     // A tile can go through TMA when it is full and its global address is 16-byte aligned.
