@@ -32,9 +32,9 @@ constexpr int NUM_VARIANTS = 8;
 //   "pipe"   = onesweep_pipelined_kernel (single sweep, persistent, look-back on a control group)
 //   "simple" = onesweep_pass_kernel (single sweep, one tile per CTA)
 const PassConfig kVariants[NUM_VARIANTS] = {
-    {"seg 2x384x16", 384, 16, 1},  {"seg 2x416x16", 416, 16, 1},  {"seg 2x384x20", 384, 20, 1},
-    {"seg 2x352x18", 352, 18, 1},  {"seg 2x448x14", 448, 14, 1},  {"seg 1x512x12 2cta", 512, 12, 2},
-    {"pipe 512x16 1cta", 512, 16, 1}, {"simple 512x16 ptx", 512, 16, 2},
+    {"seg 2x384x16", 384, 16, 1},      {"seg 2x384x20", 384, 20, 1},       {"seg 2x352x18", 352, 18, 1},
+    {"seg 1x512x12 2cta", 512, 12, 2}, {"pipe 512x16 1cta", 512, 16, 1},   {"pipe 256x24 r96/32", 256, 24, 2},
+    {"simple 512x16 ptx", 512, 16, 2}, {"simple 512x16 ballot", 512, 16, 2},
 };
 constexpr int DEFAULT_VARIANT = 0;
 
@@ -308,13 +308,13 @@ int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t
                     cudaStream_t stream) {
     switch (h->variant) {
         case 0: return launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 1: return launch_seg_t<uint32_t, false, 416, 16, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 2: return launch_seg_t<uint32_t, false, 384, 20, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 3: return launch_seg_t<uint32_t, false, 352, 18, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 4: return launch_seg_t<uint32_t, false, 448, 14, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 5: return launch_seg_t<uint32_t, false, 512, 12, 1, 2>(h, in, out, nullptr, nullptr, n, shift, stream);
-        case 6: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
-        case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 1: return launch_seg_t<uint32_t, false, 384, 20, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 2: return launch_seg_t<uint32_t, false, 352, 18, 2, 1>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 3: return launch_seg_t<uint32_t, false, 512, 12, 1, 2>(h, in, out, nullptr, nullptr, n, shift, stream);
+        case 4: return launch_pipe_t<uint32_t, false, 512, 16, 1>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 5: return launch_pipe_t<uint32_t, false, 256, 24, 2, 96, 32>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 6: return launch_pass_t<uint32_t, false, 512, 16, MATCH_PTX, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
+        case 7: return launch_pass_t<uint32_t, false, 512, 16, MATCH_BALLOT, 2>(h, in, out, nullptr, nullptr, n, shift, pass_index, stream);
         default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown kernel variant %d", h->variant);
     }
 }
