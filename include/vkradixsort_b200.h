@@ -150,9 +150,12 @@ int vkrs_partition(vkrs_handle handle, const uint32_t *keys_in, uint32_t *keys_o
  *   vkrs_ipc_alloc / vkrs_ipc_open     receive buffers shared between the ranks of one node (CUDA IPC)
  *   vkrs_partition_count               bucket counts only (the exchange plan is made from them)
  *   vkrs_partition_scatter_p2p         must follow vkrs_partition_count on the same input and handle.
- *                                      dst_tables (device, 512 x uint64): [b] = address where this rank's
- *                                      keys of bucket b start in the owner's buffer, [256 + b] the same
- *                                      for payloads (ignored without values). */
+ *                                      dst_tables (device, 1024 x uint64), per bucket b: [b] = address
+ *                                      where this rank's part of the key receive buffer of b's owner
+ *                                      starts, [256+b] the same for payloads (ignored without values),
+ *                                      [512+b] / [768+b] = first bucket / one past the last bucket of b's
+ *                                      owner (contiguous bucket ranges belong to one rank).  Inside its
+ *                                      part the sender writes one run per owner and tile. */
 int vkrs_ipc_alloc(vkrs_handle handle, uint64_t bytes, void **device_ptr, unsigned char *ipc_handle_64);
 int vkrs_ipc_open(vkrs_handle handle, const unsigned char *ipc_handle_64, void **device_ptr);
 int vkrs_ipc_close(vkrs_handle handle, void *device_ptr);

@@ -46,30 +46,23 @@ def test_plan_exchange_balances_and_is_consistent():
     assert p.send_counts == [0, 0] and p.recv_counts == [0, 0]
 
 
-def test_destination_offsets_match_the_all_to_all_layout():
-    """The fused exchange must fill the receive buffers exactly as all-to-all-v of the partitioned arrays would."""
+def test_destination_offsets():
+    """Fused exchange: every (source, owner) part of a receive buffer starts where the parts of the lower
+    source ranks end, and the parts tile the buffer exactly."""
     rng = np.random.default_rng(5)
     world = 4
     counts = rng.integers(0, 50, size=(world, 256))
     counts[:, 100:140] = 0  # empty buckets
     plans = [D.plan_exchange(counts, r) for r in range(world)]
     b = plans[0].boundaries
-    # staged layout: receive buffer of rank r = for s in ranks: for bucket in r's range: s's keys of that bucket
-    expected = {}
-    for r in range(world):
-        pos = 0
-        for s_ in range(world):
-            for bucket in range(b[r], b[r + 1]):
-                expected[(r, s_, bucket)] = pos
-                pos += int(counts[s_, bucket])
-        assert pos == sum(plans[r].recv_counts)
     for s_ in range(world):
-        owner, offset = D.destination_offsets(counts, b, s_)
+        owner, offset, first, end = D.destination_offsets(counts, b, s_)
         for bucket in range(256):
             r = int(owner[bucket])
-            assert b[r] <= bucket < b[r + 1]
-            if counts[s_, bucket] > 0:
-                assert int(offset[bucket]) == expected[(r, s_, bucket)]
+            assert b[r] <= bucket < b[r + 1] and (int(first[bucket]), int(end[bucket])) == (b[r], b[r + 1])
+            assert int(offset[bucket]) == sum(plans[r].recv_counts[:s_])
+    for r in range(world):
+        assert sum(plans[r].recv_counts) == int(counts[:, b[r]:b[r + 1]].sum())
 
 
 class NumpyOps:

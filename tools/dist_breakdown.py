@@ -47,8 +47,9 @@ for it in range(6):
     counts = ops.partition_count(buf0, n, base, shift); sync(); t.append(time.perf_counter())
     g = torch.empty(world * 256, dtype=counts.dtype, device=dev); dist.all_gather_into_tensor(g, counts)
     ac = g.view(world, 256).cpu().numpy(); plan = D.plan_exchange(ac, rank); t.append(time.perf_counter())
-    owner, offset = D.destination_offsets(ac, plan.boundaries, rank)
+    owner, offset, first, end = D.destination_offsets(ac, plan.boundaries, rank)
     tab = sorter._dst_host.numpy(); tab[:256] = np.array(sorter.peer_ptrs[0], dtype=np.int64)[owner] + 4 * offset
+    tab[512:768] = first; tab[768:1024] = end
     sorter.dst_tables.copy_(sorter._dst_host, non_blocking=True)
     ops.partition_scatter_p2p(buf0, n, base, shift, sorter.dst_tables); sync(); t.append(time.perf_counter())
     dist.barrier(); sync(); t.append(time.perf_counter())

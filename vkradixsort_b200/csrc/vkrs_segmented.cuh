@@ -146,6 +146,7 @@ struct SegGroupSmem {
     uint32_t scan_scratch[8];
     alignas(8) uint64_t full[2], empty[2];
     alignas(8) unsigned long long dst_ptr[2][RADIX];     // P2P mode: per-bucket destination arrays (keys, payloads)
+    uint32_t lex[RADIX];                                 // P2P mode: tile-local start of every bucket
 };
 
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS>
@@ -155,11 +156,14 @@ struct SegSmem {
 };
 
 // P2P == true (multi-GPU exchange fused into the partition): there is no single output array.
-// dst_tables[b] / dst_tables[256 + b] hold, for bucket b, the address where THIS rank's keys /
-// payloads of that bucket start inside the receive buffer of the rank that owns the bucket -- a
-// peer GPU's memory mapped over NVLink (or this GPU's own).  The tile is ranked and staged exactly as
-// in the local case; only the write-out addresses differ, so the exchange costs no extra pass: the
-// stores go straight over NVLink while other tiles are being ranked.
+// Contiguous ranges of buckets belong to one owner rank.  dst_tables (4 x 256 x uint64, indexed by
+// bucket b): [b] / [256+b] = address where THIS rank's part starts inside the key / payload receive
+// buffer of b's owner -- a peer GPU's memory mapped over NVLink (or this GPU's own); [512+b] / [768+b] =
+// first bucket / one past the last bucket of b's owner.  The tile is ranked and staged exactly as in
+// the local case; in the staged tile the keys of one owner are contiguous, and they are written out
+// as ONE run per owner and tile (tile-major layout inside the sender's part of the receive buffer:
+// the receiver sorts anyway, and equal keys keep their order).  Long runs are what NVLink stores
+// need; the exchange costs no extra pass and overlaps the ranking of other tiles.
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false,
           bool P2P = false>
 __global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
@@ -250,6 +254,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
 
     // ---- prologue (multi_radixsort.comp:56-77): this segment's first output index per digit ----
     uint32_t running_base = 0; // digit thread `gtid`: where the next tile's run of that digit starts
+    uint32_t owner_first = 0, owner_end = 0; // P2P: the bucket range of this digit's owner rank
     if (is_digit_thread) {
         uint32_t below = 0, total = 0;
         uint32_t g2 = 0;
@@ -275,13 +280,21 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
 #pragma unroll
         for (int w = 0; w < RADIX / 32; ++w)
             if (w < (int) dwarp) warp_prefix += s.scan_scratch[w];
-        // local output: digits are laid out one after the other; P2P: every bucket has its own array
-        running_base = P2P ? below : warp_prefix + incl - total + below;
+        // local output: digits are laid out one after the other
+        running_base = warp_prefix + incl - total + below;
         if (P2P) {
+            // one running offset per OWNER (kept redundantly by all of its digit threads): where this
+            // segment starts inside the sender's part = keys of earlier segments going to that owner
             s.dst_ptr[0][dgt] = dst_tables[dgt];
             if (HAS_VALUES) s.dst_ptr[1][dgt] = dst_tables[RADIX + dgt];
+            owner_first = (uint32_t) dst_tables[2 * RADIX + dgt];
+            owner_end = (uint32_t) dst_tables[3 * RADIX + dgt];
+            s.lex[dgt] = below;
+            named_bar_sync(bar_d, RADIX);
+            running_base = 0;
+            for (uint32_t b = owner_first; b < owner_end; ++b) running_base += s.lex[b];
         }
-        named_bar_sync(bar_d, RADIX); // scan_scratch is reused by the per-tile scan
+        named_bar_sync(bar_d, RADIX); // scan_scratch / lex are reused by the per-tile scan
     }
 
     // phase timers of worker warp 0 (tuning aid): wait-for-tile(+token), rank, barrier A, digit
@@ -385,9 +398,19 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
                 s.warp_cnt[w][dgt] = running;
                 running += c;
             }
-            s.bin_dst[slot][dgt] = running_base - local_excl;
-            // real keys only: the padding of a partial tile sits in digit 255
-            running_base += (valid != TILE && dgt == RADIX - 1) ? total - (TILE - valid) : total;
+            if (P2P) {
+                // the owner's keys form one chunk [start, end) of the staged tile -> one run in its buffer
+                s.lex[dgt] = local_excl;
+                named_bar_sync(bar_d, RADIX);
+                const uint32_t start = s.lex[owner_first];
+                const uint32_t end = owner_end == RADIX ? valid : s.lex[owner_end]; // padding sits after the real keys
+                s.bin_dst[slot][dgt] = running_base - start;
+                running_base += end - start;
+            } else {
+                s.bin_dst[slot][dgt] = running_base - local_excl;
+                // real keys only: the padding of a partial tile sits in digit 255
+                running_base += (valid != TILE && dgt == RADIX - 1) ? total - (TILE - valid) : total;
+            }
         }
         VKRS_PHASE(3)
         // ---- write tile j-1 out (overlaps the digit threads' work above) ----

@@ -3,9 +3,12 @@
 The reference is single-device; BASELINE.json config 5 defines this extension:
 N GPUs hold n keys each, the result is globally sorted with rank r holding the r-th key range.
 
-    1. key range      vkrs_key_range + all-reduce(min, max)            -> (key_base, shift)
-    2. partition      vkrs_partition: bucket(key) = min(255, (key - key_base) >> shift); the local
-                      keys come out stably grouped by bucket, with the 256 bucket counts
+    1. bucket map     bucket(key) = min(255, (key - key_base) >> shift).  First try the top byte
+                      (key_base 0, shift 24: valid for any input); only if that balances badly
+                      (narrow or skewed keys) vkrs_key_range + all-reduce(min, max) map the OCCUPIED
+                      key range onto the 256 buckets
+    2. partition      vkrs_partition: the local keys come out stably grouped by bucket, with the 256
+                      bucket counts
     3. plan           all-gather of the counts; contiguous bucket ranges are dealt to the ranks so
                       that the loads are as even as the bucket granularity allows (pure host
                       arithmetic: plan_exchange)
@@ -52,22 +55,24 @@ class ExchangePlan:
     imbalance: float   # max load / mean load over the ranks
 
 
-def destination_offsets(all_counts: np.ndarray, boundaries: list, rank: int) -> tuple[np.ndarray, np.ndarray]:
-    """For the fused exchange: (owner[b], offset[b]) = which rank owns bucket b and at which element of
-    that rank's receive buffer THIS rank's keys of bucket b start.  The receive buffer of rank r is laid
-    out source rank by source rank, each source's part bucket by bucket -- exactly what the all-to-all-v
-    of the staged path produces, so both exchanges give bit-identical buffers."""
+def destination_offsets(all_counts: np.ndarray, boundaries: list, rank: int) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """For the fused exchange, per bucket b: (owner[b], offset[b], first[b], end[b]) = the rank that owns
+    b, the element of that rank's receive buffer where THIS rank's part starts, and the owner's bucket
+    range [first, end).  The receive buffer of rank r is laid out source rank by source rank; inside a
+    source's part the keys come tile by tile in the sender's order (the receiver sorts anyway)."""
     all_counts = np.asarray(all_counts, dtype=np.int64)
     world = all_counts.shape[0]
     owner = np.zeros(NUM_BUCKETS, dtype=np.int64)
     offset = np.zeros(NUM_BUCKETS, dtype=np.int64)
+    first = np.zeros(NUM_BUCKETS, dtype=np.int64)
+    end = np.zeros(NUM_BUCKETS, dtype=np.int64)
     for r in range(world):
         lo, hi = boundaries[r], boundaries[r + 1]
         owner[lo:hi] = r
-        before_me = int(all_counts[:rank, lo:hi].sum())  # parts of the lower source ranks
-        mine = all_counts[rank, lo:hi]
-        offset[lo:hi] = before_me + np.concatenate([[0], np.cumsum(mine)[:-1]]) if hi > lo else 0
-    return owner, offset
+        offset[lo:hi] = int(all_counts[:rank, lo:hi].sum())  # parts of the lower source ranks
+        first[lo:hi] = lo
+        end[lo:hi] = hi
+    return owner, offset, first, end
 
 
 def plan_exchange(all_counts: np.ndarray, rank: int) -> ExchangePlan:
@@ -159,6 +164,8 @@ class DistributedSorter:
         self.last_plan: ExchangePlan | None = None
         self.exchange_bytes = 0
         self.used_p2p = False
+        self.used_key_range = False
+        self.max_imbalance = 1.10  # above this the top-byte buckets are replaced by buckets over the occupied key range
         self._ipc_owned, self._ipc_opened = [], []
         self._alloc()
 
@@ -197,8 +204,8 @@ class DistributedSorter:
                 self.recv[0] = t
             else:
                 self.recv_vals[0] = t
-        self.dst_tables = torch.zeros(2 * NUM_BUCKETS, dtype=torch.int64, device=self.device)
-        self._dst_host = torch.zeros(2 * NUM_BUCKETS, dtype=torch.int64).pin_memory()
+        self.dst_tables = torch.zeros(4 * NUM_BUCKETS, dtype=torch.int64, device=self.device)
+        self._dst_host = torch.zeros(4 * NUM_BUCKETS, dtype=torch.int64).pin_memory()
 
     def _release_p2p(self):
         if self._ipc_opened or self._ipc_owned:
@@ -232,24 +239,32 @@ class DistributedSorter:
             self.last_plan = None
             return (keys, values) if values is not None else keys
 
-        # 1. occupied key range over all ranks
-        mm = self.ops.key_range(keys, n)
-        t = torch.stack([mm[0], -mm[1]])
-        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
-        kmin, neg_kmax = (int(x) for x in t.tolist())
-        key_base, shift = choose_bucket_map(kmin, -neg_kmax)
+        def count_and_gather(key_base, shift):
+            # bucket counts (fused exchange) or the whole stable partition (staged exchange), then
+            # everybody's counts.  The all-gather also orders this step after every rank's previous
+            # local sort, so the receive buffers are free to be overwritten.
+            if self.p2p:
+                counts = self.ops.partition_count(keys, n, key_base, shift, values is not None)
+            else:
+                counts = self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
+            gathered = torch.empty(self.world * NUM_BUCKETS, dtype=counts.dtype, device=counts.device)
+            dist.all_gather_into_tensor(gathered, counts, group=self.group)
+            return gathered.view(self.world, NUM_BUCKETS).cpu().numpy()
 
-        # 2. bucket counts (fused exchange) or the whole stable partition (staged exchange)
-        if self.p2p:
-            counts = self.ops.partition_count(keys, n, key_base, shift, values is not None)
-        else:
-            counts = self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
-
-        # 3. plan from everybody's bucket counts.  The all-gather also orders this step after every
-        #    rank's previous local sort, so the receive buffers are free to be overwritten.
-        gathered = torch.empty(self.world * NUM_BUCKETS, dtype=counts.dtype, device=counts.device)
-        dist.all_gather_into_tensor(gathered, counts, group=self.group)
-        all_counts = gathered.view(self.world, NUM_BUCKETS).cpu().numpy()
+        # 1+2+3. Speculate that the keys use the full 32-bit range: bucket = top byte is valid for ANY
+        # input (it only may balance badly), and it saves the key-range pass and one host round trip.
+        key_base, shift = 0, 24
+        all_counts = count_and_gather(key_base, shift)
+        self.used_key_range = False
+        if plan_exchange(all_counts, self.rank).imbalance > self.max_imbalance:
+            # narrow or skewed keys: map the OCCUPIED range onto the 256 buckets and count again
+            mm = self.ops.key_range(keys, n)
+            t = torch.stack([mm[0], -mm[1]])
+            dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+            kmin, neg_kmax = (int(x) for x in t.tolist())
+            key_base, shift = choose_bucket_map(kmin, -neg_kmax)
+            all_counts = count_and_gather(key_base, shift)
+            self.used_key_range = True
         plan = plan_exchange(all_counts, self.rank)
         self.last_plan = plan
         total_recv = sum(plan.recv_counts)
@@ -264,11 +279,13 @@ class DistributedSorter:
 
         # 4. exchange
         if fused:
-            owner, offset = destination_offsets(all_counts, plan.boundaries, self.rank)
+            owner, offset, first, end = destination_offsets(all_counts, plan.boundaries, self.rank)
             tab = self._dst_host.numpy()
             for which in range(2 if values is not None else 1):
                 base = np.array(self.peer_ptrs[which], dtype=np.int64)[owner]
                 tab[which * NUM_BUCKETS:(which + 1) * NUM_BUCKETS] = base + 4 * offset
+            tab[2 * NUM_BUCKETS:3 * NUM_BUCKETS] = first
+            tab[3 * NUM_BUCKETS:4 * NUM_BUCKETS] = end
             self.dst_tables.copy_(self._dst_host, non_blocking=True)
             self.ops.partition_scatter_p2p(keys, n, key_base, shift, self.dst_tables, values)
             dist.barrier(group=self.group)  # every rank's stores have landed before anybody sorts
