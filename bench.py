@@ -113,6 +113,14 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def common_config(pairs: bool, world: int, n: int) -> dict:
+    """The part of `config` both arms report identically."""
+    return {"workload": ("10^8 uint32 key + uint32 payload pairs" if pairs else "10^8 random uint32 keys")
+            + ", multi_radixsort (BASELINE.json configs[%d])" % (2 if pairs else 1)
+            + (", per GPU; global sort by bucket exchange" if world > 1 else ""),
+            "keys_per_gpu": n, "distribution": "uniform full-range uint32 (numpy PCG64)", "seed": SEED}
+
+
 def make_keys(n: int, seed: int) -> np.ndarray:
     """Uniform full-range uint32 (BASELINE.json 'random uint32'); numpy PCG64, fixed seed."""
     return np.random.default_rng(seed).integers(0, 1 << 32, size=n, dtype=np.uint32)
@@ -151,8 +159,7 @@ def run_reference(args) -> int:
         "impl": "reference", "metric": METRIC, "value": mkeys, "unit": "Mkeys/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "10^8 random uint32 keys, multi_radixsort (BASELINE.json configs[1])",
-                   "distribution": "uniform full-range uint32", "seed": SEED},
+        "config": {**common_config(False, 1, N_KEYS), "sample_keys_per_step": sample},
         "cpu_baseline": {"value": mkeys, "unit": "Mkeys/s", "cores": threads, "kind": "port",
                          "sample": f"{sample} of the 10^8 keys per step, restated multi_radixsort shaders "
                                    f"(oracle/vkrs_oracle.c, nb={nb}), OpenMP over work groups",
@@ -362,11 +369,7 @@ def run_b200(args) -> int:
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
             "data": "synthetic",
-            "config": {"workload": ("10^8 uint32 key + uint32 payload pairs" if pairs else "10^8 random uint32 keys")
-                       + ", multi_radixsort (BASELINE.json configs[%d])" % (2 if pairs else 1) +
-                       (", per GPU; global sort by bucket exchange" if world > 1 else ""),
-                       "keys_per_gpu": n, "distribution": "uniform full-range uint32 (numpy PCG64)",
-                       "seed": SEED, "l2": "inputs (400 MB) larger than L2 (126 MB); input restored by a "
+            "config": {**common_config(pairs, world, n), "l2": "inputs (400 MB) larger than L2 (126 MB); input restored by a "
                        "400 MB device copy before every step", "variant": capi.variant_name(handle.variant),
                        "timing": "CUDA events on the launch stream around each sort, summed; max over ranks"},
             "clocks": clocks, "gpu_launches": int(launches), "verified": bool(verified),

@@ -92,3 +92,13 @@ def test_product_never_imports_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and "oracle" not in text, (
                     f"{os.path.join(dirpath, f)} mentions the oracle; the product path must not depend on it")
+
+
+def test_cpp_facade_and_examples_build(built_lib):
+    """include/vkradixsort_b200.hpp (the reference's class names over the C-ABI) and the two example
+    programs compile and link against the library (running them needs a GPU: -m gpu)."""
+    import subprocess
+
+    subprocess.run(["make", "-C", os.path.join(ROOT, "examples"), "-s"], check=True)
+    for exe in ("multiradixsortexample", "singleradixsortexample"):
+        assert os.access(os.path.join(ROOT, "vkradixsort_b200", "bin", exe), os.X_OK)

@@ -374,3 +374,25 @@ def test_two_gpu_bucket_exchange():
                         os.path.join(root, "tests", "dist_gpu_worker.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST_OK" in r.stdout
+
+
+def test_config5_single_gpu_size_properties(handle, dev):
+    """BASELINE.json config 5 at G=1: 8 x 10^8 keys on one GPU (3.2 GB per buffer), checked through
+    size-independent properties on the device: sortedness and the multiset checksum."""
+    from vkradixsort_b200 import capi
+
+    n = 800_000_000
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED0005)
+    b0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=gen)
+    sum_in = int(b0.to(torch.int64).sum())
+    b1 = torch.empty_like(b0)
+    handle.multi_sort(b0, b1, None, capi.multi_push_constants(n, 32))
+    handle.check_device_error()
+    del b1
+    flip = torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
+    for c in range(0, n, 1 << 28):
+        x = b0[c:min(n, c + (1 << 28) + 1)] ^ flip
+        assert bool((x[1:] >= x[:-1]).all()), f"not sorted in chunk starting at {c}"
+        del x
+    assert int(b0.to(torch.int64).sum()) == sum_in
