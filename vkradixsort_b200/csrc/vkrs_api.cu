@@ -39,7 +39,7 @@ const PassConfig kVariants[NUM_VARIANTS] = {
 constexpr int DEFAULT_VARIANT = 0;
 
 // default configurations of the other paths
-constexpr int PAIR_WORKERS = 256, PAIR_KPT = 16; // segmented path, two worker groups per CTA
+constexpr int PAIR_WORKERS = 352, PAIR_KPT = 16; // segmented path, two worker groups per CTA
 constexpr int U64_WORKERS = 256, U64_KPT = 16;
 constexpr int STAGED_THREADS = 256, STAGED_KPT = 16;
 constexpr int SINGLE_THREADS = 1024, SINGLE_KPT = 8;

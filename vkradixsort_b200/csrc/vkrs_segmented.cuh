@@ -138,7 +138,6 @@ struct SegGroupSmem {
     static constexpr int WARPS = WORKERS / 32;
     static constexpr int TILE = WORKERS * KPT;
     alignas(128) KeyT in[2][TILE];                       // TMA destinations (tile j, j+1 of the segment)
-    alignas(128) uint32_t vin[HAS_VALUES ? 2 : 1][HAS_VALUES ? TILE : 4];
     alignas(128) KeyT sorted[TILE];                      // tile in digit order, staged for the write-out
     alignas(128) uint32_t sorted_v[HAS_VALUES ? TILE : 4];
     uint32_t warp_cnt[WARPS][RADIX];                     // per-warp digit counters, then exclusive bases
@@ -222,9 +221,8 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
                 if (tile_is_tma(tile)) {
                     const uint64_t base = (uint64_t) tile * TILE;
                     constexpr uint32_t kbytes = TILE * sizeof(KeyT);
-                    mbar_arrive_expect_tx(&s.full[slot], kbytes + (HAS_VALUES ? TILE * 4u : 0u));
+                    mbar_arrive_expect_tx(&s.full[slot], kbytes);
                     bulk_copy_g2s(s.in[slot], keys_in + base, kbytes, &s.full[slot]);
-                    if (HAS_VALUES) bulk_copy_g2s(s.vin[slot], vals_in + base, TILE * 4u, &s.full[slot]);
                 } else {
                     mbar_arrive(&s.full[slot]); // the workers copy this tile in themselves
                 }
@@ -343,7 +341,6 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             // rank after every real key, at tile positions >= valid.
             for (uint32_t p = gtid; p < TILE; p += WORKERS) {
                 s.in[slot][p] = p < valid ? ld_stream(keys_in + tile_base + p) : ~KeyT(0);
-                if (HAS_VALUES) s.vin[slot][p] = p < valid ? ld_stream(vals_in + tile_base + p) : 0u;
             }
             named_bar_sync(bar_w, WORKERS);
         }
@@ -373,6 +370,17 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             __syncwarp();
             d_cur = d_next;
             peers_cur = peers_next;
+        }
+        // Payloads do not go through the shared-memory ring: they are needed once, at the scatter, so
+        // each thread fetches its own (coalesced, warp-striped like the keys) straight into registers
+        // now and the loads complete under the digit section and the write-out of tile j-1.
+        uint32_t vreg[HAS_VALUES ? KPT : 1];
+        if (HAS_VALUES) {
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                const uint32_t idx = chunk0 + i * 32;
+                vreg[i] = (valid == TILE || idx < valid) ? ld_stream(vals_in + tile_base + idx) : 0u;
+            }
         }
         VKRS_PHASE(1)
         named_bar_sync(bar_w, WORKERS); // (A) all warp counters final; sorted[] holds tile j-1 completely
@@ -437,11 +445,8 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
 #pragma unroll
             for (int i = 0; i < SB; ++i) s.sorted[rb[i]] = kb[i];
             if (HAS_VALUES) {
-                uint32_t vb[SB];
 #pragma unroll
-                for (int i = 0; i < SB; ++i) vb[i] = s.vin[slot][chunk0 + (i0 + i) * 32];
-#pragma unroll
-                for (int i = 0; i < SB; ++i) s.sorted_v[rb[i]] = vb[i];
+                for (int i = 0; i < SB; ++i) s.sorted_v[rb[i]] = vreg[i0 + i];
             }
         }
         __syncwarp();
