@@ -116,6 +116,14 @@ int vkrs_multi_sort_pairs(vkrs_handle handle, uint32_t *keys0, uint32_t *keys1, 
 int vkrs_multi_sort_u64(vkrs_handle handle, uint64_t *buf0, uint64_t *buf1, uint32_t *histograms,
                         const vkrs_multi_push_constants *pc, void *stream);
 
+/* Signed / floating-point keys.  The reference sorts unsigned keys only and tells callers to
+ * preprocess negatives themselves (README.md:98-99,154-155); here the order-preserving transform is
+ * fused into the first pass's reads and undone in the last pass's writes: same traffic as u32.
+ * F32 order: by value, -0.0 before +0.0, NaNs at the two ends according to their sign bit. */
+typedef enum vkrs_key_type { VKRS_KEY_U32 = 0, VKRS_KEY_I32 = 1, VKRS_KEY_F32 = 2 } vkrs_key_type;
+int vkrs_multi_sort_typed(vkrs_handle handle, void *buf0, void *buf1, uint32_t *histograms,
+                          const vkrs_multi_push_constants *pc, int key_type, void *stream);
+
 /* The reference loop run literally through the per-stage entry points (4 x histograms +
  * scatter with the caller's tiling); kept so the staged path can be timed and compared. */
 int vkrs_multi_sort_staged(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,

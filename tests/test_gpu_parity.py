@@ -396,3 +396,35 @@ def test_config5_single_gpu_size_properties(handle, dev):
         assert bool((x[1:] >= x[:-1]).all()), f"not sorted in chunk starting at {c}"
         del x
     assert int(b0.to(torch.int64).sum()) == sum_in
+
+
+def test_typed_keys_signed_and_float(handle, dev, oracle):
+    """Fused key transforms: int32 and float32 keys sort by value with the same
+    four passes; exact against numpy on the same bits."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(77)
+    for n in (1, 1000, 8193, 300_001, 2_000_003):
+        pc = capi.multi_push_constants(n, 32)
+        ints = rng.integers(-(1 << 31), 1 << 31, size=n, dtype=np.int64).astype(np.int32)
+        b0 = torch.from_numpy(ints.copy()).to(dev)
+        handle.multi_sort_typed(b0, scratch_like(b0), None, pc, capi.KEY_I32)
+        assert np.array_equal(b0.cpu().numpy(), np.sort(ints)), n
+        f = rng.standard_normal(n).astype(np.float32) * np.float32(1e6)
+        f[:: 7] = 0.0
+        f[1:: 11] = -0.0
+        f[2:: 13] = np.inf
+        f[3:: 17] = -np.inf
+        b0 = torch.from_numpy(f.copy()).to(dev)
+        handle.multi_sort_typed(b0, torch.empty_like(b0), None, pc, capi.KEY_F32)
+        got = b0.cpu().numpy()
+        bits = f.view(np.uint32)
+        ordered = np.where(bits >> 31, ~bits, bits | np.uint32(0x80000000))  # the same order-preserving map, on the host
+        expect = f[np.argsort(ordered, kind="stable")]
+        assert np.array_equal(got.view(np.uint32), expect.view(np.uint32)), n
+        assert np.array_equal(got, np.sort(f))  # and it is numpy's value order (no NaNs here)
+        u = oracle.generate_random(n, 31 + n, 0xFFFFFFFF)
+        b0 = to_dev(u, dev)
+        handle.multi_sort_typed(b0, scratch_like(b0), None, pc, capi.KEY_U32)
+        assert np.array_equal(to_host(b0), np.sort(u))
+    handle.check_device_error()

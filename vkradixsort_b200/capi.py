@@ -19,6 +19,8 @@ VKRS_ERR_CUDA = -2
 VKRS_ERR_UNSUPPORTED = -3
 VKRS_ERR_INTERNAL = -4
 
+KEY_U32, KEY_I32, KEY_F32 = 0, 1, 2
+
 WORKGROUP_SIZE = 256
 RADIX_SORT_BINS = 256
 
@@ -27,7 +29,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_create", "vkrs_destroy", "vkrs_last_error", "vkrs_version",
     "vkrs_global_invocation_size", "vkrs_workgroup_count",
     "vkrs_multi_histograms", "vkrs_multi_scatter", "vkrs_multi_pass",
-    "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged",
+    "vkrs_multi_sort", "vkrs_multi_sort_pairs", "vkrs_multi_sort_u64", "vkrs_multi_sort_staged", "vkrs_multi_sort_typed",
     "vkrs_single_sort", "vkrs_sort_auto", "vkrs_multi_sort_host", "vkrs_key_range", "vkrs_partition",
     "vkrs_partition_count", "vkrs_partition_scatter_p2p", "vkrs_ipc_alloc", "vkrs_ipc_open", "vkrs_ipc_close", "vkrs_ipc_free",
     "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
@@ -90,6 +92,7 @@ def load() -> ctypes.CDLL:
         "vkrs_multi_sort_pairs": (i32, [vp, vp, vp, vp, vp, vp, mpc, vp]),
         "vkrs_multi_sort_u64": (i32, [vp, vp, vp, vp, mpc, vp]),
         "vkrs_multi_sort_staged": (i32, [vp, vp, vp, vp, mpc, vp]),
+        "vkrs_multi_sort_typed": (i32, [vp, vp, vp, vp, mpc, i32, vp]),
         "vkrs_single_sort": (i32, [vp, vp, vp, spc, vp]),
         "vkrs_sort_auto": (i32, [vp, vp, vp, u32, vp]),
         "vkrs_multi_sort_host": (i32, [vp, vp, u32, vp]),
@@ -226,6 +229,11 @@ class Handle:
     def multi_sort_u64(self, buf0, buf1, histograms, pc: MultiPushConstants, stream=None):
         self._check(self._lib.vkrs_multi_sort_u64(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms),
                                                   ctypes.byref(pc), _stream(stream)))
+
+    def multi_sort_typed(self, buf0, buf1, histograms, pc: MultiPushConstants, key_type: int, stream=None):
+        """key_type: KEY_U32 / KEY_I32 / KEY_F32."""
+        self._check(self._lib.vkrs_multi_sort_typed(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms), ctypes.byref(pc),
+                                                    key_type, _stream(stream)))
 
     def multi_sort_staged(self, buf0, buf1, histograms, pc: MultiPushConstants, stream=None):
         self._check(self._lib.vkrs_multi_sort_staged(self._h, _ptr(buf0), _ptr(buf1), _ptr(histograms),

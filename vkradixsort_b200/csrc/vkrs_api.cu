@@ -260,13 +260,14 @@ int launch_pipe_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vi
 // One digit pass of the segmented path: count (one CTA per segment), then the persistent scatter.
 // do_count / do_scatter let the multi-GPU path run the two halves separately (the exchange plan is
 // made from the counts in between); dst_tables != nullptr selects the peer-to-peer write-out.
-template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false, bool P2P = false>
+template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false, bool P2P = false,
+          int XF_IN = 0, int XF_OUT = 0>
 int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
                  uint32_t shift, cudaStream_t stream, uint32_t key_base = 0, uint32_t *bucket_totals = nullptr,
                  bool do_count = true, bool do_scatter = true, const unsigned long long *dst_tables = nullptr) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     constexpr uint32_t TILE = Smem::Group::TILE;
-    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION, P2P>;
+    auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION, P2P, XF_IN, XF_OUT>;
     static thread_local int configured_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (configured_device != h->device) {
@@ -287,7 +288,7 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     if (do_count) {
         {
             LaunchScope scope(h, "segment_histogram_kernel", stream);
-            VKRS_CUDA(h, launch_pdl(segment_histogram_kernel<KeyT, PARTITION>, dim3(segments), dim3(SEGHIST_THREADS), 0, stream, in, n, shift,
+            VKRS_CUDA(h, launch_pdl(segment_histogram_kernel<KeyT, PARTITION, XF_IN>, dim3(segments), dim3(SEGHIST_THREADS), 0, stream, in, n, shift,
                                     key_base, TILE, tiles, h->seg_hist));
         }
         if (bucket_totals) {
@@ -302,6 +303,19 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
+}
+
+// Typed keys: the order-preserving transform is applied as pass 0 reads the keys and undone as the
+// last pass writes them -- no extra pass, no extra traffic.
+template <int XF>
+int typed_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cudaStream_t s) {
+    int r = launch_seg_t<uint32_t, false, 384, 16, 2, 1, false, false, XF, 0>(h, buf0, buf1, nullptr, nullptr, n, 0, s);
+    if (r) return r;
+    r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, buf1, buf0, nullptr, nullptr, n, 8, s);
+    if (r) return r;
+    r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, buf0, buf1, nullptr, nullptr, n, 16, s);
+    if (r) return r;
+    return launch_seg_t<uint32_t, false, 384, 16, 2, 1, false, false, 0, XF>(h, buf1, buf0, nullptr, nullptr, n, 24, s);
 }
 
 int launch_pass_u32(vkrs_context *h, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t shift, int pass_index,
@@ -697,6 +711,25 @@ int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *his
         if (r) return r;
     }
     return VKRS_OK;
+}
+
+int vkrs_multi_sort_typed(vkrs_handle h, void *buf0, void *buf1, uint32_t *histograms, const vkrs_multi_push_constants *pc,
+                          int key_type, void *stream) {
+    (void) histograms;
+    int r = check_multi_pc(h, pc, false);
+    if (r) return r;
+    const uint32_t n = pc->g_num_elements;
+    if (n == 0) return VKRS_OK;
+    if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint32_t *b0 = static_cast<uint32_t *>(buf0), *b1 = static_cast<uint32_t *>(buf1);
+    switch (key_type) {
+        case VKRS_KEY_U32: return typed_sort_u32<0>(h, b0, b1, n, s);
+        case VKRS_KEY_I32: return typed_sort_u32<1>(h, b0, b1, n, s);
+        case VKRS_KEY_F32: return typed_sort_u32<2>(h, b0, b1, n, s);
+        default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown key type %d", key_type);
+    }
 }
 
 int vkrs_multi_sort_pairs(vkrs_handle h, uint32_t *keys0, uint32_t *keys1, uint32_t *values0, uint32_t *values1,

@@ -91,8 +91,8 @@ onesweep_pipelined_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ k
     static_assert(GROUPS == 1 || GROUPS == 2, "one worker group, or two in ping-pong");
     static_assert(WORKERS >= RADIX && WORKERS % 128 == 0, "whole warpgroups of workers, one thread per digit");
     static_assert(TILE <= 65536 && KPT % 2 == 0, "tile ranks are stored in 16 bits, two per register");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw_pipe[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw_pipe);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t num_tiles = (uint32_t) (((uint64_t) n + TILE - 1) / TILE);

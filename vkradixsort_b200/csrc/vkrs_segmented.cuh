@@ -52,6 +52,25 @@ struct DigitOf {
     __device__ __forceinline__ DigitBitMasks bit_masks() const { return DigitBitMasks(PARTITION ? 0u : (shift & 31u)); }
 };
 
+// Order-preserving key transforms fused into the first / last pass (the reference leaves signed and
+// floating-point keys to caller-side preprocessing, README.md:98-99,154-155).  fwd maps the key type's
+// order onto unsigned order, inv undoes it.  XF: 0 = unsigned (identity), 1 = two's-complement signed,
+// 2 = IEEE-754 binary32/binary64 (negative values reversed, -0 < +0, NaNs at the two ends by sign).
+template <typename KeyT, int XF>
+struct KeyXform {
+    static constexpr KeyT SIGN = KeyT(1) << (8 * sizeof(KeyT) - 1);
+    static __device__ __forceinline__ KeyT fwd(KeyT k) {
+        if (XF == 1) return k ^ SIGN;
+        if (XF == 2) return k ^ ((k & SIGN) ? ~KeyT(0) : SIGN);
+        return k;
+    }
+    static __device__ __forceinline__ KeyT inv(KeyT k) {
+        if (XF == 1) return k ^ SIGN;
+        if (XF == 2) return k ^ ((k & SIGN) ? SIGN : ~KeyT(0));
+        return k;
+    }
+};
+
 // Tiles [first, first + count) of segment g when `num_tiles` tiles are dealt to `num_segments`
 // segments as evenly as possible (host and device agree through this one function).
 __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_segments, uint32_t num_tiles,
@@ -68,7 +87,7 @@ __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_
 // =====================================================================================
 constexpr int SEGHIST_THREADS = 512;
 
-template <typename KeyT, bool PARTITION>
+template <typename KeyT, bool PARTITION, int XF_IN = 0>
 __global__ void __launch_bounds__(SEGHIST_THREADS)
 segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t key_base,
                          uint32_t tile_keys, uint32_t num_tiles, uint32_t *__restrict__ hist) {
@@ -81,7 +100,7 @@ segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shi
     if (hi > n) hi = n;
     const DigitOf<KeyT, PARTITION> digit(shift, key_base);
     uint32_t *my_col = cnt + lane;
-    auto count_key = [&](KeyT k) { atomicAdd(my_col + digit(k) * 32, 1u); };
+    auto count_key = [&](KeyT k) { atomicAdd(my_col + digit(KeyXform<KeyT, XF_IN>::fwd(k)) * 32, 1u); };
     for (int i = tid; i < RADIX * 32; i += SEGHIST_THREADS) cnt[i] = 0;
     grid_dependency_wait(); // programmatic dependent launch: everything above overlaps the previous kernel's tail
     __syncthreads();
@@ -163,8 +182,10 @@ struct SegSmem {
 // as ONE run per owner and tile (tile-major layout inside the sender's part of the receive buffer:
 // the receiver sorts anyway, and equal keys keep their order).  Long runs are what NVLink stores
 // need; the exchange costs no extra pass and overlaps the ranking of other tiles.
+// XF_IN / XF_OUT: key transform applied to every key as it is read (first pass of a typed sort) /
+// undone as it is written (last pass); see KeyXform.
 template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int MIN_BLOCKS, bool PARTITION = false,
-          bool P2P = false>
+          bool P2P = false, int XF_IN = 0, int XF_OUT = 0>
 __global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
 segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                          const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
@@ -178,8 +199,8 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
     static_assert(GROUPS >= 1 && GROUPS <= 4, "1..4 worker groups per CTA");
     static_assert(WORKERS >= RADIX && WORKERS % 32 == 0, "one worker thread per digit is required");
     static_assert(TILE <= 65536 && KPT % 2 == 0, "tile ranks are stored in 16 bits, two per register");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw_seg[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw_seg);
 
     const int tid = threadIdx.x, lane = tid & 31;
     const uint32_t num_segments = gridDim.x * GROUPS;
@@ -316,10 +337,10 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             const uint32_t g = s.bin_dst[pslot][d] + p;
             if (full || p < valid) {
                 if (P2P) {
-                    reinterpret_cast<KeyT *>(s.dst_ptr[0][d])[g] = k;
+                    reinterpret_cast<KeyT *>(s.dst_ptr[0][d])[g] = KeyXform<KeyT, XF_OUT>::inv(k);
                     if (HAS_VALUES) reinterpret_cast<uint32_t *>(s.dst_ptr[1][d])[g] = s.sorted_v[p];
                 } else {
-                    keys_out[g] = k;
+                    keys_out[g] = KeyXform<KeyT, XF_OUT>::inv(k);
                     if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
                 }
             }
@@ -340,7 +361,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             // keys become all-ones: digit 255 at every shift and last in memory order, so they
             // rank after every real key, at tile positions >= valid.
             for (uint32_t p = gtid; p < TILE; p += WORKERS) {
-                s.in[slot][p] = p < valid ? ld_stream(keys_in + tile_base + p) : ~KeyT(0);
+                s.in[slot][p] = p < valid ? ld_stream(keys_in + tile_base + p) : KeyXform<KeyT, XF_IN>::inv(~KeyT(0));
             }
             named_bar_sync(bar_w, WORKERS);
         }
@@ -353,13 +374,14 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
         uint32_t rank2[KPT / 2];
         // Software-pipelined: the ballots of round i+1 are issued before the counter update of
         // round i, so the shared-memory round trip of one round hides behind the votes of the next.
-        uint32_t d_cur = digit(tin[chunk0]);
-        uint32_t peers_cur = match_key_table(digit.match_word(tin[chunk0], d_cur), d_cur, bm, lc);
+        const KeyT key0 = KeyXform<KeyT, XF_IN>::fwd(tin[chunk0]);
+        uint32_t d_cur = digit(key0);
+        uint32_t peers_cur = match_key_table(digit.match_word(key0, d_cur), d_cur, bm, lc);
 #pragma unroll
         for (int i = 0; i < KPT; ++i) {
             uint32_t d_next = 0, peers_next = 0;
             if (i + 1 < KPT) {
-                const KeyT key = tin[chunk0 + (i + 1) * 32];
+                const KeyT key = KeyXform<KeyT, XF_IN>::fwd(tin[chunk0 + (i + 1) * 32]);
                 d_next = digit(key);
                 peers_next = match_key_table(digit.match_word(key, d_next), d_next, bm, lc);
             }
@@ -434,7 +456,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
             KeyT kb[SB];
             uint32_t rb[SB];
 #pragma unroll
-            for (int i = 0; i < SB; ++i) kb[i] = tin[chunk0 + (i0 + i) * 32];
+            for (int i = 0; i < SB; ++i) kb[i] = KeyXform<KeyT, XF_IN>::fwd(tin[chunk0 + (i0 + i) * 32]);
 #pragma unroll
             for (int i = 0; i < SB; ++i) rb[i] = my_cnt[digit(kb[i])];
 #pragma unroll
