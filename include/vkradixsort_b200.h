@@ -101,8 +101,10 @@ int vkrs_multi_pass(vkrs_handle handle, const uint32_t *elements_in, uint32_t *e
  * Four 8-bit digit passes, buf0 -> buf1 -> buf0 -> buf1 -> buf0.  pc->g_shift is ignored
  * (the loop sets 0,8,16,24, :57-58); g_num_workgroups / g_num_blocks_per_workgroup describe
  * the caller's histogram buffer (capacity g_num_workgroups*256 uint32, may be NULL) and are
- * otherwise only validated: this entry is free to use its own tiling (fused Onesweep
- * schedule: one 4x256 histogram kernel + 4 single-pass chained-scan scatter kernels). */
+ * otherwise only validated: this entry is free to use its own tiling.  Default schedule: per digit
+ * one segment histogram kernel + one persistent, TMA-fed scatter kernel (the reference's own two-stage
+ * decomposition with 2 x #SMs segments); the single-sweep chained-scan ("Onesweep") schedules are
+ * selectable with vkrs_set_variant -- DESIGN.md 4.1 / 4.2. */
 int vkrs_multi_sort(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
                     const vkrs_multi_push_constants *pc, void *stream);
 
@@ -182,8 +184,8 @@ int vkrs_multi_sort_host(vkrs_handle handle, uint32_t *host_keys, uint32_t num_e
  * returns VKRS_ERR_INTERNAL if any kernel since the last check raised the flag. ---- */
 int vkrs_check_device_error(vkrs_handle handle, void *stream);
 
-/* ---- tuning hooks: pick one of the precompiled tile configurations of the fused keys-only
- * pass kernel (also settable with the VKRS_VARIANT environment variable at create time). */
+/* ---- tuning hooks: pick one of the precompiled schedules / tile configurations of the keys-only
+ * whole sort (also settable with the VKRS_VARIANT environment variable at create time). */
 int vkrs_num_variants(void);
 const char *vkrs_variant_name(int variant);
 int vkrs_set_variant(vkrs_handle handle, int variant);
@@ -208,7 +210,7 @@ int vkrs_debug_counters(vkrs_handle handle, int enable, uint64_t *out);
 /* ---- introspection for tests / benches ---- */
 /* Number of kernel launches the handle has enqueued since creation. */
 uint64_t vkrs_launch_count(vkrs_handle handle);
-/* Tile size (keys per CTA step) of the fused multi path. */
+/* Tile size (keys per worker group and step) of the default whole-sort schedule. */
 uint32_t vkrs_tile_size(void);
 
 #ifdef __cplusplus

@@ -20,7 +20,7 @@ namespace {
 
 using namespace vkrs;
 
-// ---- fused-path kernel configurations (selectable for tuning runs) ----------------------
+// ---- whole-sort schedules / tile configurations (selectable for tuning runs) --------------
 struct PassConfig {
     const char *name;
     int threads, kpt, min_blocks;
@@ -690,7 +690,7 @@ int vkrs_multi_sort_staged(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32
 
 int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
                     const vkrs_multi_push_constants *pc, void *stream) {
-    (void) histograms; // the fused schedule keeps its tile status in the handle's workspace
+    (void) histograms; // the whole-sort schedules keep their histogram rows / tile status in the handle's workspace
     int r = check_multi_pc(h, pc, false);
     if (r) return r;
     const uint32_t n = pc->g_num_elements;

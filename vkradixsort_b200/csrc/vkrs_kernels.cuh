@@ -1,6 +1,8 @@
 // vkrs_kernels.cuh -- all __global__ kernels of the B200 radix sort.
 //
-// Fused path (vkrs_multi_sort*):      global_histogram_kernel -> NUM_PASSES x onesweep_pass_kernel
+// Default whole sort:                 vkrs_segmented.cuh (segment_histogram_kernel + segmented_scatter_kernel)
+// Single-sweep variants ("simple"):   global_histogram_kernel -> NUM_PASSES x onesweep_pass_kernel
+//                        ("pipe"):    global_histogram_kernel -> NUM_PASSES x onesweep_pipelined_kernel (vkrs_pipeline.cuh)
 // Staged path (per-stage C-ABI):      staged_histograms_kernel | staged_colsum/chunkscan/offsets + staged_scatter_kernel
 // Single-workgroup path:              single_sort_kernel
 #pragma once
