@@ -191,6 +191,40 @@ const char *vkrs_variant_name(int variant);
 int vkrs_set_variant(vkrs_handle handle, int variant);
 int vkrs_get_variant(vkrs_handle handle);
 
+/* ---- schedules of the keys-only whole sort (vkrs_multi_sort / vkrs_sort_auto / vkrs_multi_sort_host; also
+ * settable with the VKRS_SCHEDULE environment variable at create time).  Every schedule produces the
+ * same bytes in buf0 (a sorted uint32 array is unique, MultiRadixSort.cpp:148-161); they differ in how
+ * much work per key the SMs do:
+ *   LSD                  four stable 8-bit passes, least significant digit first -- the literal
+ *                        MultiRadixSort::execute loop (MultiRadixSort.cpp:56-61).
+ *   LSD_UNSTABLE_FIRST   the same, but pass 0 ranks keys with one shared-memory atomic instead of the
+ *                        stable ballot match: a first pass has no earlier order to preserve.
+ *   BUCKET               two unstable passes on the two most significant digits (below the keys' common
+ *                        leading zero bits), then every 16-bit-prefix bucket is sorted in shared memory.
+ *                        Falls back to LSD on the device, without a host round trip, when a bucket is
+ *                        larger than 4096 keys (heavily skewed input).  DESIGN.md 4.1.
+ *   AUTO                 BUCKET for large N, LSD_UNSTABLE_FIRST for medium N, LSD below (and whenever a
+ *                        tuning variant other than the default was selected with vkrs_set_variant).
+ * Key+payload, 64-bit and typed sorts always run stable LSD passes. */
+typedef enum vkrs_schedule {
+    VKRS_SCHEDULE_AUTO = 0,
+    VKRS_SCHEDULE_LSD = 1,
+    VKRS_SCHEDULE_LSD_UNSTABLE_FIRST = 2,
+    VKRS_SCHEDULE_BUCKET = 3,
+    VKRS_NUM_SCHEDULES = 4
+} vkrs_schedule;
+int vkrs_set_schedule(vkrs_handle handle, int schedule);
+int vkrs_get_schedule(vkrs_handle handle);
+const char *vkrs_schedule_name(int schedule);
+/* Control words of the handle's last BUCKET sort, for tests and diagnostics: out8 = {shift of pass 1,
+ * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, OR of all
+ * keys, largest bucket seen if > 2048, pieces of pass 1, pieces of pass 2}.  Synchronises `stream`. */
+int vkrs_bucket_stats(vkrs_handle handle, uint32_t *out8, void *stream);
+/* Test aid: end the BUCKET schedule after stage 1 (partition pass 1: keys grouped by the top digit, in
+ * buf1), 2 (pass 2: grouped by the top two digits, in buf0) or 3 (local sort, fallback passes not
+ * enqueued) so that every stage can be compared with the oracle; 0 = whole schedule (default). */
+int vkrs_debug_bucket_stop(vkrs_handle handle, int stage);
+
 /* ---- opt-in per-kernel timing (the reference only has a wall clock around the loop,
  * MultiRadixSort.cpp:49,63-65).  While enabled every kernel launch is bracketed by a CUDA event
  * pair on its stream.  vkrs_profile_collect() synchronises the device, folds the pairs into

@@ -1,0 +1,186 @@
+"""GPU parity tests of the keys-only schedules that rank without stability (run with -m gpu):
+the bucket schedule (two unstable top-digit partition passes + shared-memory sort of every
+16-bit-prefix bucket, vkrs_msd.cuh) and the LSD schedule with an unstable first pass.
+
+Bar: bit-exact against std::sort / numpy, the reference's own criterion
+(multiradixsort/src/MultiRadixSort.cpp:148-161); the intermediate stages are checked through the
+properties that define them (a permutation of the input, grouped by the partition digits).
+Nothing here reads /root/reference.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture()
+def handle(built_lib):
+    from vkradixsort_b200 import Handle
+
+    h = Handle(0, 1 << 20)
+    yield h
+    h.close()
+
+
+def to_dev(a, dev):
+    return torch.from_numpy(a.view(np.int32)).to(dev)
+
+
+def to_host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def run_sort(handle, keys, dev, schedule, stop=0):
+    from vkradixsort_b200 import capi
+
+    n = keys.shape[0]
+    b0 = to_dev(keys, dev)
+    b1 = torch.full_like(b0, 0x5A5A5A5A)  # poisoned scratch
+    handle.set_schedule(schedule)
+    handle.debug_bucket_stop(stop)
+    handle.multi_sort(b0, b1, None, capi.multi_push_constants(n, 32))
+    handle.check_device_error()
+    handle.debug_bucket_stop(0)
+    return to_host(b0), to_host(b1)
+
+
+def distributions(oracle, n, seed):
+    ar = np.arange(n, dtype=np.uint64)
+    rng = np.random.default_rng(seed)
+    return {
+        "uniform32": oracle.generate_random(n, seed, 0xFFFFFFFF),
+        "reference28": oracle.generate_random(n, seed + 1, 0x0FFFFFFF),  # MultiRadixSort.cpp:126
+        "bits20": oracle.generate_random(n, seed + 2, 0x000FFFFF),
+        "bits12": oracle.generate_random(n, seed + 3, 0x00000FFF),
+        "bits5": oracle.generate_random(n, seed + 4, 31),
+        "sorted": (ar * 4294967295 // max(n, 1)).astype(np.uint32),
+        "descending": (0xFFFFFFFF - ar * 4294967295 // max(n, 1)).astype(np.uint32),
+        "all_equal": np.full(n, 0xDEADBEEF, dtype=np.uint32),
+        "zeros": np.zeros(n, dtype=np.uint32),
+        "max": np.full(n, 0xFFFFFFFF, dtype=np.uint32),
+        "two_valued": ((ar % 2) * 0xFFFFFFFF).astype(np.uint32),
+        "hot_prefix": np.where(rng.random(n) < 0.5, np.uint32(0xABCD0000), 0).astype(np.uint32)
+        | rng.integers(0, 1 << 16, n, dtype=np.uint32),  # half of the keys in one 16-bit-prefix bucket
+        "low16_only_high_random": (rng.integers(0, 1 << 16, n, dtype=np.uint32) << 16).astype(np.uint32),
+    }
+
+
+BUCKET_SIZES = [1, 2, 33, 255, 4096, 6143, 6144, 6145, 12289, 100_003, 1_000_001, 5_000_011]
+
+
+@pytest.mark.parametrize("n", BUCKET_SIZES)
+def test_bucket_schedule_matches_std_sort(handle, dev, oracle, n):
+    from vkradixsort_b200 import capi
+
+    for name, keys in distributions(oracle, n, 4242 + n).items():
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+        assert oracle.test_sort(np.sort(keys), out) == -1, f"n={n} {name} {handle.bucket_stats()}"
+
+
+@pytest.mark.parametrize("n", [1, 6145, 100_003, 1 << 20, 3_000_001])
+def test_lsd_unstable_first_pass_matches_std_sort(handle, dev, oracle, n):
+    from vkradixsort_b200 import capi
+
+    for name, keys in distributions(oracle, n, 99 + n).items():
+        keys = np.ascontiguousarray(keys, dtype=np.uint32)
+        out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_LSD_UNSTABLE_FIRST)
+        assert oracle.test_sort(np.sort(keys), out) == -1, f"n={n} {name}"
+
+
+def test_bucket_stages(handle, dev, oracle):
+    """Stage by stage: pass 1 leaves a permutation of the input grouped by the top digit in buffer 1,
+    pass 2 one grouped by the top two digits in buffer 0, the local sort finishes it."""
+    from vkradixsort_b200 import capi
+
+    n = 2_000_003
+    for name, max_value, s1 in (("uniform32", 0xFFFFFFFF, 24), ("reference28", 0x0FFFFFFF, 20)):
+        keys = oracle.generate_random(n, 555, max_value)
+        _, b1 = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=1)
+        st = handle.bucket_stats()
+        assert st["shift1"] == s1 and st["shift2"] == s1 - 8, (name, st)
+        assert st["recount"] == (1 if s1 != 24 else 0), (name, st)
+        d1 = (b1 >> np.uint32(s1)) & np.uint32(255)
+        assert np.all(np.diff(d1.astype(np.int64)) >= 0), f"{name}: pass 1 output is not grouped by the top digit"
+        assert np.array_equal(np.sort(b1), np.sort(keys)), f"{name}: pass 1 output is not a permutation of the input"
+        b0, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=2)
+        d12 = (b0 >> np.uint32(s1 - 8)).astype(np.int64)
+        assert np.all(np.diff(d12) >= 0), f"{name}: pass 2 output is not grouped by the top two digits"
+        assert np.array_equal(np.sort(b0), np.sort(keys)), f"{name}: pass 2 output is not a permutation of the input"
+        b0, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=3)
+        assert handle.bucket_stats()["fallback"] == 0, name
+        assert oracle.test_sort(np.sort(keys), b0) == -1, f"{name}: local sort"
+
+
+def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
+    """A 16-bit-prefix bucket above 4096 keys cannot be finished in shared memory: the device raises
+    the fallback word and the stable LSD passes behind the schedule sort the array."""
+    from vkradixsort_b200 import capi
+
+    n = 300_000
+    rng = np.random.default_rng(7)
+    keys = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
+    out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["fallback"] == 1 and st["max_bucket"] > 4096, st
+    assert np.array_equal(out, np.sort(keys))
+    # the same keys spread over many prefixes: no fallback
+    keys2 = oracle.generate_random(n, 8, 0xFFFFFFFF)
+    out2, _ = run_sort(handle, keys2, dev, capi.SCHEDULE_BUCKET)
+    assert handle.bucket_stats()["fallback"] == 0
+    assert np.array_equal(out2, np.sort(keys2))
+    # all keys equal and no low bits left to sort: nothing to fall back for
+    keys3 = np.full(n, 0xFF00, dtype=np.uint32)
+    out3, _ = run_sort(handle, keys3, dev, capi.SCHEDULE_BUCKET)
+    assert np.array_equal(out3, keys3)
+
+
+def test_bucket_workspace_reuse_and_unaligned(handle, dev, oracle):
+    """Sizes going up and down on one handle (the pass-1 piece table is cached per N) and key buffers
+    that start at a 4-byte, not 16-byte, aligned address (no TMA: the workers copy the tiles in)."""
+    from vkradixsort_b200 import capi
+
+    handle.set_schedule(capi.SCHEDULE_BUCKET)
+    for i, n in enumerate([700_001, 9_000, 700_001, 1_500_000, 3, 700_001]):
+        keys = oracle.generate_random(n, 300 + i, 0xFFFFFFFF)
+        out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+        assert np.array_equal(out, np.sort(keys)), n
+    n = 250_001
+    for off in (1, 2, 3):
+        keys = oracle.generate_random(n, 70 + off, 0xFFFFFFFF)
+        big0 = torch.zeros(n + 8, dtype=torch.int32, device=dev)
+        big1 = torch.zeros(n + 8, dtype=torch.int32, device=dev)
+        big0[off:off + n] = to_dev(keys, dev)
+        handle.multi_sort(big0[off:], big1[off:], None, capi.multi_push_constants(n, 32))
+        handle.check_device_error()
+        assert np.array_equal(to_host(big0[off:off + n]), np.sort(keys)), off
+        assert int(big0[:off].abs().sum()) == 0 and int(big0[off + n:].abs().sum()) == 0, "wrote outside the buffer"
+
+
+def test_auto_schedule_picks_bucket_for_large_n(handle, dev, oracle):
+    """6*10^7 keys through the default (auto) schedule: sortedness + multiset checksum on the device,
+    then element-wise against numpy."""
+    from vkradixsort_b200 import capi
+
+    n = 60_000_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(2024)
+    b0 = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+    keys = to_host(b0)
+    b1 = torch.empty_like(b0)
+    handle.set_schedule(capi.SCHEDULE_AUTO)
+    launches0 = handle.launch_count
+    handle.multi_sort(b0, b1, None, capi.multi_push_constants(n, 32))
+    handle.check_device_error()
+    st = handle.bucket_stats()
+    assert st["shift1"] == 24 and st["fallback"] == 0 and st["pieces2"] > 0, st
+    assert handle.launch_count - launches0 >= 8
+    assert np.array_equal(to_host(b0), np.sort(keys))

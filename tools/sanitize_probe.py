@@ -26,4 +26,15 @@ for n in (1, 1000, 50_001, 200_003):
         assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k))
     mm = torch.zeros(2, dtype=torch.int32, device=dev); cnt = torch.zeros(256, dtype=torch.int32, device=dev)
     h.key_range(dv(k), n, mm); h.partition(dv(k), torch.empty(n, dtype=torch.int32, device=dev), n, 0, 24, cnt); torch.cuda.synchronize()
+# the schedules that rank without stability (vkrs_msd.cuh): uniform, 28-bit (moved digit window + recount),
+# 12-bit (no local sort) and one-bucket keys (device-side fallback to the LSD passes)
+for sched in (capi.SCHEDULE_LSD_UNSTABLE_FIRST, capi.SCHEDULE_BUCKET):
+    h.set_schedule(sched)
+    for n in (1, 1000, 6145, 50_001, 200_003):
+        for mask, base in ((0xFFFFFFFF, 0), (0x0FFFFFFF, 0), (0xFFF, 0), (0xFFFF, 0x12340000)):
+            k = (rng.integers(0, 1 << 32, size=n, dtype=np.uint32) & np.uint32(mask)) | np.uint32(base)
+            b0 = dv(k); b1 = torch.empty_like(b0)
+            h.multi_sort(b0, b1, None, capi.multi_push_constants(n, 32)); torch.cuda.synchronize()
+            assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)), (sched, n, hex(mask))
+h.set_schedule(capi.SCHEDULE_AUTO)
 print("SANITIZE_PROBE_OK")

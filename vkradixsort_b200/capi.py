@@ -35,7 +35,13 @@ EXPORTED_SYMBOLS = [
     "vkrs_check_device_error", "vkrs_num_variants", "vkrs_variant_name", "vkrs_set_variant", "vkrs_get_variant",
     "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
+    "vkrs_set_schedule", "vkrs_get_schedule", "vkrs_schedule_name", "vkrs_bucket_stats",
+    "vkrs_debug_bucket_stop",
 ]
+
+# vkrs_schedule (include/vkradixsort_b200.h)
+SCHEDULE_AUTO, SCHEDULE_LSD, SCHEDULE_LSD_UNSTABLE_FIRST, SCHEDULE_BUCKET = 0, 1, 2, 3
+NUM_SCHEDULES = 4
 
 
 class MultiPushConstants(ctypes.Structure):
@@ -116,6 +122,11 @@ def load() -> ctypes.CDLL:
                                      ctypes.POINTER(u64)]),
         "vkrs_launch_count": (u64, [vp]),
         "vkrs_tile_size": (u32, []),
+        "vkrs_set_schedule": (i32, [vp, i32]),
+        "vkrs_get_schedule": (i32, [vp]),
+        "vkrs_schedule_name": (ctypes.c_char_p, [i32]),
+        "vkrs_bucket_stats": (i32, [vp, ctypes.POINTER(u32), vp]),
+        "vkrs_debug_bucket_stop": (i32, [vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -296,6 +307,25 @@ class Handle:
     def variant(self) -> int:
         return int(self._lib.vkrs_get_variant(self._h))
 
+    def set_schedule(self, schedule: int):
+        """SCHEDULE_AUTO / SCHEDULE_LSD / SCHEDULE_LSD_UNSTABLE_FIRST / SCHEDULE_BUCKET (keys-only whole sort)."""
+        self._check(self._lib.vkrs_set_schedule(self._h, schedule))
+
+    @property
+    def schedule(self) -> int:
+        return int(self._lib.vkrs_get_schedule(self._h))
+
+    def bucket_stats(self, stream=None) -> dict:
+        """Control words of the last bucket-schedule sort (synchronises the stream)."""
+        out = (ctypes.c_uint32 * 8)()
+        self._check(self._lib.vkrs_bucket_stats(self._h, out, _stream(stream)))
+        names = ("shift1", "shift2", "fallback", "recount", "key_or", "max_bucket", "pieces1", "pieces2")
+        return dict(zip(names, (int(v) for v in out)))
+
+    def debug_bucket_stop(self, stage: int):
+        """Test aid: end the bucket schedule after stage 1 / 2 / 3 (0 = whole schedule)."""
+        self._check(self._lib.vkrs_debug_bucket_stop(self._h, stage))
+
     def debug_counters(self, enable: bool) -> list:
         out = (ctypes.c_uint64 * 32)()
         self._check(self._lib.vkrs_debug_counters(self._h, 1 if enable else 0, out))
@@ -328,6 +358,10 @@ def num_variants() -> int:
 
 def variant_name(v: int) -> str:
     return (load().vkrs_variant_name(v) or b"").decode()
+
+
+def schedule_name(s: int) -> str:
+    return (load().vkrs_schedule_name(s) or b"").decode()
 
 
 def tile_size() -> int:

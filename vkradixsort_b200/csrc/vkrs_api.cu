@@ -5,6 +5,7 @@
 // sm_100a kernels of vkrs_kernels.cuh or returns an error.
 #include "../../include/vkradixsort_b200.h"
 #include "vkrs_kernels.cuh"
+#include "vkrs_msd.cuh"
 #include "vkrs_pipeline.cuh"
 #include "vkrs_segmented.cuh"
 
@@ -94,6 +95,13 @@ struct vkrs_context {
     // vkrs_multi_sort_host device buffers
     uint32_t *host_buf[2] = {nullptr, nullptr};
     uint64_t host_cap = 0;
+
+    // keys-only whole-sort schedule (vkrs_set_schedule) and the bucket schedule's workspace (vkrs_msd.cuh)
+    int schedule = 0; // VKRS_SCHEDULE_AUTO
+    unsigned char *msd_ws = nullptr;
+    uint32_t msd_segments_cap = 0; // segments the workspace was laid out for
+    uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
+    int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
 };
 
 namespace {
@@ -264,7 +272,8 @@ template <typename KeyT, bool HAS_VALUES, int WORKERS, int KPT, int GROUPS, int 
           int XF_IN = 0, int XF_OUT = 0>
 int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin, uint32_t *vout, uint32_t n,
                  uint32_t shift, cudaStream_t stream, uint32_t key_base = 0, uint32_t *bucket_totals = nullptr,
-                 bool do_count = true, bool do_scatter = true, const unsigned long long *dst_tables = nullptr) {
+                 bool do_count = true, bool do_scatter = true, const unsigned long long *dst_tables = nullptr,
+                 const uint32_t *gate = nullptr) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     constexpr uint32_t TILE = Smem::Group::TILE;
     auto kernel = segmented_scatter_kernel<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS, MIN_BLOCKS, PARTITION, P2P, XF_IN, XF_OUT>;
@@ -289,7 +298,7 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
         {
             LaunchScope scope(h, "segment_histogram_kernel", stream);
             VKRS_CUDA(h, launch_pdl(segment_histogram_kernel<KeyT, PARTITION, XF_IN>, dim3(segments), dim3(SEGHIST_THREADS), 0, stream, in, n, shift,
-                                    key_base, TILE, tiles, h->seg_hist));
+                                    key_base, TILE, tiles, h->seg_hist, gate));
         }
         if (bucket_totals) {
             LaunchScope scope(h, "segment_column_sum_kernel", stream);
@@ -299,7 +308,7 @@ int launch_seg_t(vkrs_context *h, const KeyT *in, KeyT *out, const uint32_t *vin
     if (do_scatter) {
         LaunchScope scope(h, P2P ? "segmented_scatter_kernel<p2p>" : HAS_VALUES ? "segmented_scatter_kernel<pairs>" : (sizeof(KeyT) == 8 ? "segmented_scatter_kernel<u64>" : "segmented_scatter_kernel"), stream);
         VKRS_CUDA(h, launch_pdl(kernel, dim3(ctas), dim3(GROUPS * WORKERS + 32), sizeof(Smem), stream, in, out, vin, vout, n, shift,
-                                key_base, (const uint32_t *) h->seg_hist, tiles, h->debug_counters, dst_tables));
+                                key_base, (const uint32_t *) h->seg_hist, tiles, h->debug_counters, dst_tables, gate));
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
@@ -363,6 +372,203 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
         LaunchScope scope(h, "global_histogram_kernel", stream);
         kernel<<<(unsigned) grid, HIST_THREADS, smem, stream>>>(keys, n, (uint32_t) per_cta, h->ctrl,
                                                                  h->ctrl + vkrs_context::CTRL_DONE);
+    }
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+// ---- the bucket schedule (vkrs_msd.cuh) -------------------------------------------------------
+constexpr int MSD_WORKERS = 384, MSD_KPT = 16, MSD_GROUPS = 2;
+constexpr uint32_t MSD_TILE = MSD_WORKERS * MSD_KPT;
+constexpr uint32_t MSD_SUBS = RADIX * RADIX;          // (digit1, digit2) buckets
+constexpr uint32_t AUTO_MSD_MIN = 48u << 20;          // vkrs_multi_sort, schedule auto: bucket schedule from here
+constexpr uint32_t AUTO_UNSTABLE_FIRST_MIN = 1u << 20; // ... below it: LSD with an unstable first pass from here
+
+// Workspace of the bucket schedule, laid out for `segments` segments.
+struct MsdWorkspace {
+    MsdPlan *plan;
+    uint4 *pieces[2];
+    uint32_t *seg_first[2], *bucket_first[2];
+    uint32_t *bucket_start; // 257: starts of the 256 buckets of pass 1
+    uint32_t *sub_start;    // 65537: starts of the (digit1, digit2) buckets
+    uint32_t *hist[2];
+    size_t bytes;
+    MsdWorkspace(unsigned char *base, uint32_t segments) {
+        const size_t max_pieces = (size_t) segments + RADIX;
+        size_t off = 0;
+        auto take = [&](size_t b) {
+            const size_t at = off;
+            off += (b + 255) / 256 * 256;
+            return base + at;
+        };
+        plan = reinterpret_cast<MsdPlan *>(take(sizeof(MsdPlan)));
+        for (int p = 0; p < 2; ++p) {
+            pieces[p] = reinterpret_cast<uint4 *>(take(max_pieces * sizeof(uint4)));
+            seg_first[p] = reinterpret_cast<uint32_t *>(take(((size_t) segments + 1) * sizeof(uint32_t)));
+            bucket_first[p] = reinterpret_cast<uint32_t *>(take((RADIX + 1) * sizeof(uint32_t)));
+            hist[p] = reinterpret_cast<uint32_t *>(take(max_pieces * RADIX * sizeof(uint32_t)));
+        }
+        bucket_start = reinterpret_cast<uint32_t *>(take((RADIX + 1) * sizeof(uint32_t)));
+        sub_start = reinterpret_cast<uint32_t *>(take(((size_t) MSD_SUBS + 1) * sizeof(uint32_t)));
+        bytes = off;
+    }
+};
+
+using MsdScatterSmem = MsdSmem<MSD_WORKERS, MSD_KPT, MSD_GROUPS>;
+
+int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments, uint32_t &seg_keys) {
+    auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>;
+    static thread_local int configured_device = -1;
+    static thread_local int blocks_per_sm = 0;
+    if (configured_device != h->device) {
+        int r = set_smem(h, kernel, sizeof(MsdScatterSmem));
+        if (r) return r;
+        r = set_smem(h, msd_local_sort_kernel, sizeof(LocalSmem));
+        if (r) return r;
+        VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, MSD_GROUPS * MSD_WORKERS + 32, sizeof(MsdScatterSmem)));
+        if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "bucket scatter kernel does not fit on an SM");
+        configured_device = h->device;
+    }
+    const uint32_t tiles = (uint32_t) (((uint64_t) n + MSD_TILE - 1) / MSD_TILE);
+    ctas = (uint32_t) (h->sm_count * blocks_per_sm);
+    const uint32_t need = (tiles + MSD_GROUPS - 1) / MSD_GROUPS;
+    if (ctas > need) ctas = need;
+    if (ctas == 0) ctas = 1;
+    segments = ctas * MSD_GROUPS;
+    if (segments > (uint32_t) MSD_PLAN_THREADS) return fail(h, VKRS_ERR_INTERNAL, "%u segments: the piece planner takes at most %d", segments, MSD_PLAN_THREADS);
+    // a whole number of tiles per segment: every full tile of pass 1 is 16-byte aligned for TMA
+    const uint32_t tiles_per_seg = (tiles + segments - 1) / segments;
+    seg_keys = tiles_per_seg * MSD_TILE;
+    if (!h->msd_ws || segments > h->msd_segments_cap) {
+        const uint32_t cap = (uint32_t) (h->sm_count * blocks_per_sm * MSD_GROUPS);
+        VKRS_CUDA(h, cudaDeviceSynchronize());
+        if (h->msd_ws) VKRS_CUDA(h, cudaFree(h->msd_ws));
+        h->msd_ws = nullptr;
+        h->msd_plan_n = 0;
+        const size_t bytes = MsdWorkspace(nullptr, cap).bytes;
+        void *p = nullptr;
+        VKRS_CUDA(h, cudaMalloc(&p, bytes));
+        VKRS_CUDA(h, cudaMemset(p, 0, bytes));
+        h->msd_ws = static_cast<unsigned char *>(p);
+        h->msd_segments_cap = cap;
+    }
+    return VKRS_OK;
+}
+
+// init + (cached per N) the piece table of the first pass: pieces == segments, one bucket [0, n)
+int msd_begin(vkrs_context *h, const MsdWorkspace &w, uint32_t n, uint32_t segments, uint32_t seg_keys, uint32_t shift0,
+              uint32_t shift1, cudaStream_t s) {
+    {
+        LaunchScope scope(h, "msd_init_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_init_kernel, dim3(1), dim3(32), 0, s, w.plan, shift0, shift1));
+    }
+    if (h->msd_plan_n != n || h->msd_plan_segments != segments || h->msd_plan_seg_keys != seg_keys) {
+        LaunchScope scope(h, "msd_plan_pieces_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_plan_pieces_kernel, dim3(1), dim3(MSD_PLAN_THREADS), 0, s, (const uint32_t *) nullptr, 1u, n, seg_keys,
+                                segments, w.pieces[0], w.seg_first[0], w.bucket_first[0], &w.plan->num_pieces[0], (uint32_t *) nullptr));
+        h->msd_plan_n = n;
+        h->msd_plan_segments = segments;
+        h->msd_plan_seg_keys = seg_keys;
+    }
+    return VKRS_OK;
+}
+
+// Keys-only sort, least significant digit first, whose FIRST pass is the unstable scatter: a first
+// pass has no earlier order to keep.  buf0 -> buf1 -> buf0 -> buf1 -> buf0 as MultiRadixSort.cpp:34-62.
+int lsd_unstable_first_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cudaStream_t s) {
+    uint32_t ctas, segments, seg_keys;
+    int r = msd_prepare(h, n, ctas, segments, seg_keys);
+    if (r) return r;
+    const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
+    r = msd_begin(h, w, n, segments, seg_keys, 0, 0, s);
+    if (r) return r;
+    {
+        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
+                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
+                                (const uint32_t *) nullptr));
+    }
+    {
+        LaunchScope scope(h, "msd_scatter_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>, dim3(ctas), dim3(MSD_GROUPS * MSD_WORKERS + 32),
+                                sizeof(MsdScatterSmem), s, (const uint32_t *) buf0, buf1, n, w.plan, 0, (const uint4 *) w.pieces[0],
+                                (const uint32_t *) w.seg_first[0], (const uint32_t *) w.bucket_first[0], (const uint32_t *) nullptr,
+                                (const uint32_t *) w.hist[0], (uint32_t *) nullptr, 0u));
+    }
+    for (int p = 1; p < 4; ++p) {
+        uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
+        r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s);
+        if (r) return r;
+    }
+    return VKRS_OK;
+}
+
+// The bucket schedule (see vkrs_msd.cuh).  Result in buf0.
+int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cudaStream_t s) {
+    uint32_t ctas, segments, seg_keys;
+    int r = msd_prepare(h, n, ctas, segments, seg_keys);
+    if (r) return r;
+    const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
+    r = msd_begin(h, w, n, segments, seg_keys, 24, 16, s);
+    if (r) return r;
+    auto scatter = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>;
+    const dim3 sblock(MSD_GROUPS * MSD_WORKERS + 32);
+    // ---- pass 1: top digit, whole array = one bucket ----
+    {
+        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<true>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
+                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
+                                (const uint32_t *) nullptr));
+    }
+    {
+        LaunchScope scope(h, "msd_window_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_window_kernel, dim3(1), dim3(32), 0, s, w.plan));
+    }
+    { // only works when the keys have leading zero bits (the digit window moved)
+        LaunchScope scope(h, "msd_piece_histogram_kernel<recount>", s);
+        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
+                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
+                                (const uint32_t *) &w.plan->recount));
+    }
+    {
+        LaunchScope scope(h, "msd_scatter_kernel", s);
+        VKRS_CUDA(h, launch_pdl(scatter, dim3(ctas), sblock, sizeof(MsdScatterSmem), s, (const uint32_t *) buf0, buf1, n, w.plan, 0,
+                                (const uint4 *) w.pieces[0], (const uint32_t *) w.seg_first[0], (const uint32_t *) w.bucket_first[0],
+                                (const uint32_t *) nullptr, (const uint32_t *) w.hist[0], w.bucket_start, 0u));
+    }
+    if (h->msd_stop_after == 1) return VKRS_OK;
+    // ---- pass 2: second digit inside each of the 256 buckets ----
+    {
+        LaunchScope scope(h, "msd_plan_pieces_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_plan_pieces_kernel, dim3(1), dim3(MSD_PLAN_THREADS), 0, s, (const uint32_t *) w.bucket_start, (uint32_t) RADIX,
+                                n, seg_keys, segments, w.pieces[1], w.seg_first[1], w.bucket_first[1], &w.plan->num_pieces[1], w.sub_start));
+    }
+    {
+        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments + RADIX), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf1,
+                                (const uint4 *) w.pieces[1], (const uint32_t *) &w.plan->num_pieces[1], w.plan, 1, w.hist[1],
+                                (const uint32_t *) nullptr));
+    }
+    {
+        LaunchScope scope(h, "msd_scatter_kernel", s);
+        VKRS_CUDA(h, launch_pdl(scatter, dim3(ctas), sblock, sizeof(MsdScatterSmem), s, (const uint32_t *) buf1, buf0, n, w.plan, 1,
+                                (const uint4 *) w.pieces[1], (const uint32_t *) w.seg_first[1], (const uint32_t *) w.bucket_first[1],
+                                (const uint32_t *) w.bucket_start, (const uint32_t *) w.hist[1], w.sub_start, (uint32_t) LOCAL_MAX));
+    }
+    if (h->msd_stop_after == 2) return VKRS_OK;
+    // ---- every (digit1, digit2) bucket sorted in shared memory, in place ----
+    {
+        LaunchScope scope(h, "msd_local_sort_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_local_sort_kernel, dim3((unsigned) (h->sm_count * 4)), dim3(LOCAL_THREADS), sizeof(LocalSmem), s, buf0,
+                                (const uint32_t *) w.sub_start, MSD_SUBS, (const MsdPlan *) w.plan));
+    }
+    if (h->msd_stop_after == 3) return VKRS_OK;
+    // ---- fallback: four stable LSD passes that only work if some bucket was too large ----
+    for (int p = 0; p < 4; ++p) {
+        uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
+        r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s, 0, nullptr, true, true, nullptr,
+                                                         &w.plan->fallback);
+        if (r) return r;
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
@@ -495,6 +701,10 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         int iv = atoi(v);
         if (iv >= 0 && iv < NUM_VARIANTS) h->variant = iv;
     }
+    if (const char *v = getenv("VKRS_SCHEDULE")) {
+        int iv = atoi(v);
+        if (iv >= 0 && iv < VKRS_NUM_SCHEDULES) h->schedule = iv;
+    }
     void *p = nullptr;
     e = cudaMalloc(&p, vkrs_context::CTRL_WORDS * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(p, 0, vkrs_context::CTRL_WORDS * sizeof(uint32_t));
@@ -536,6 +746,7 @@ int vkrs_destroy(vkrs_handle h) {
     cudaFree(h->debug_counters);
     cudaFree(h->host_buf[0]);
     cudaFree(h->host_buf[1]);
+    cudaFree(h->msd_ws);
     delete h;
     return VKRS_OK;
 }
@@ -615,6 +826,50 @@ int vkrs_set_variant(vkrs_handle h, int variant) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (variant < 0 || variant >= NUM_VARIANTS) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "variant %d out of range", variant);
     h->variant = variant;
+    return VKRS_OK;
+}
+
+int vkrs_set_schedule(vkrs_handle h, int schedule) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (schedule < 0 || schedule >= VKRS_NUM_SCHEDULES) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "schedule %d out of range", schedule);
+    h->schedule = schedule;
+    return VKRS_OK;
+}
+
+int vkrs_get_schedule(vkrs_handle h) { return h ? h->schedule : -1; }
+
+const char *vkrs_schedule_name(int schedule) {
+    switch (schedule) {
+        case VKRS_SCHEDULE_AUTO: return "auto";
+        case VKRS_SCHEDULE_LSD: return "lsd (4 stable passes)";
+        case VKRS_SCHEDULE_LSD_UNSTABLE_FIRST: return "lsd, unstable first pass";
+        case VKRS_SCHEDULE_BUCKET: return "bucket (2 unstable top-digit passes + local sort)";
+        default: return "";
+    }
+}
+
+// Control words of the last bucket-schedule sort: {shift1, shift2, fallback, recount, key_or, max_sub,
+// pieces of pass 1, pieces of pass 2}.  Synchronises `stream`.
+int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!out8) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "out8 is NULL");
+    static_assert(sizeof(MsdPlan) == 8 * sizeof(uint32_t), "vkrs_bucket_stats copies the plan as 8 words");
+    memset(out8, 0, 8 * sizeof(uint32_t));
+    if (!h->msd_ws) return VKRS_OK;
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, sizeof(MsdPlan), cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaStreamSynchronize(s));
+    return VKRS_OK;
+}
+
+// Test aid: end the bucket schedule early so each stage can be checked on its own.
+//   1 = after partition pass 1 (keys grouped by the top digit in buf1), 2 = after pass 2 (grouped by the top
+//   two digits in buf0), 3 = after the local sort (no fallback passes), 0 = whole schedule.
+int vkrs_debug_bucket_stop(vkrs_handle h, int stage) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (stage < 0 || stage > 3) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "stage %d out of range", stage);
+    h->msd_stop_after = stage;
     return VKRS_OK;
 }
 
@@ -698,6 +953,13 @@ int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *his
     if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int sched = h->schedule;
+    if (sched == VKRS_SCHEDULE_AUTO) {
+        if (h->variant != DEFAULT_VARIANT) sched = VKRS_SCHEDULE_LSD; // a tuning variant was picked: run exactly that kernel
+        else sched = n >= AUTO_MSD_MIN ? VKRS_SCHEDULE_BUCKET : (n >= AUTO_UNSTABLE_FIRST_MIN ? VKRS_SCHEDULE_LSD_UNSTABLE_FIRST : VKRS_SCHEDULE_LSD);
+    }
+    if (sched == VKRS_SCHEDULE_BUCKET) return msd_sort_u32(h, buf0, buf1, n, s);
+    if (sched == VKRS_SCHEDULE_LSD_UNSTABLE_FIRST) return lsd_unstable_first_sort_u32(h, buf0, buf1, n, s);
     if (!variant_is_segmented(h->variant)) { // the single-sweep variants need the global digit starts
         const uint32_t tile = variant_tile(h->variant);
         r = ensure_status(h, ((uint64_t) n + tile - 1) / tile);

@@ -1,0 +1,676 @@
+// vkrs_msd.cuh -- the keys-only "bucket" schedule: two most-significant-digit partition passes that
+// do NOT have to be stable, then every 16-bit-prefix bucket is finished inside shared memory.
+//
+// Why: on B200 the stable digit pass (vkrs_segmented.cuh) is bound by the SM, not by HBM: ranking a
+// key *stably* inside a warp costs 8 ballots + two nibble tables + two shuffles (~40 instructions
+// per 32 keys) and three bank-conflicted shared-memory accesses.  Stability is what a
+// least-significant-digit sort needs from every pass but its first.  A most-significant-digit split
+// needs none: the order inside a bucket is irrelevant because the bucket is sorted completely
+// afterwards.  Without stability a key's place in its tile is ONE shared-memory atomic
+// (rank = atomicAdd(count[digit], 1)), ~3x fewer instructions per key.  The result of a keys-only
+// sort is unique, so the output is bit-identical to the reference's (testSort:
+// multiradixsort/src/MultiRadixSort.cpp:148-161).  Key+payload sorts keep the stable LSD passes.
+//
+// Schedule for N keys (8-bit digits as in multi_radixsort.comp:12,100; `top` = highest set bit of
+// the OR of all keys, so leading zero bits -- the reference's 28-bit test keys,
+// MultiRadixSort.cpp:126 -- cost nothing):
+//   pass 1   digit (key >> s1) & 255, s1 = top-7 : piece histogram + unstable scatter  buf0 -> buf1
+//   pass 2   digit (key >> s2) & 255, s2 = s1-8, inside each of the 256 buckets of pass 1
+//                                                : piece histogram + unstable scatter  buf1 -> buf0
+//   local    every (digit1, digit2) bucket (N / 65536 keys on average) is sorted by its remaining low
+//            bits inside shared memory, in place in buf0 : one unstable + one stable 8-bit pass.
+// A "piece" is the part of one bucket that lies inside one segment (a contiguous slab of the array
+// owned by one worker group): the reference's "work group w owns nb*256 consecutive keys"
+// (multi_radixsort_histograms.comp:43) cut at bucket boundaries, because a most-significant-digit
+// pass must keep every key inside its bucket.  Row q of the histogram matrix belongs to piece q
+// (multi_radixsort_histograms.comp:53-55), and the scatter's prologue turns the rows of ONE bucket
+// into that piece's first output index per digit (multi_radixsort.comp:56-77, restricted to the bucket).
+//
+// The schedule depends on the key distribution: a (digit1, digit2) bucket larger than LOCAL_MAX keys
+// cannot be finished in shared memory.  That is detected on the device while pass 2 runs (the bucket
+// sizes fall out of its prologue); the plan's `fallback` word is raised, the local sort does nothing
+// and the four stable LSD passes that are enqueued behind it -- and otherwise exit at once -- sort
+// buf0.  No host round trip, everything stays stream-ordered.
+#pragma once
+#include "vkrs_async.cuh"
+#include "vkrs_common.cuh"
+
+namespace vkrs {
+
+// Device-resident control words of one bucket-schedule sort.
+struct MsdPlan {
+    uint32_t shift[2];      // digit shift of partition pass 1 / 2; shift[1] is also the number of low bits left to the local sort
+    uint32_t fallback;      // != 0: some bucket is too large for the local sort -> the stable LSD passes run
+    uint32_t recount;       // != 0: the pass-1 histogram was counted at the wrong shift and is counted again
+    uint32_t key_or;        // OR of all keys (only gathered by the first histogram)
+    uint32_t max_sub;       // diagnostic: size of the largest (digit1, digit2) bucket seen
+    uint32_t num_pieces[2]; // pieces of pass 1 / 2 (NOT reset per sort: the pass-1 plan is cached per N)
+};
+
+constexpr int MSD_PLAN_THREADS = 1024;
+constexpr int MSD_HIST_THREADS = 512;
+constexpr int LOCAL_THREADS = 256;
+constexpr int LOCAL_KPT = 16;
+constexpr int LOCAL_MAX = LOCAL_THREADS * LOCAL_KPT; // largest bucket the local sort takes
+
+__device__ __forceinline__ uint32_t msd_digit(uint32_t key, uint32_t shift) { return (key >> shift) & (RADIX - 1); }
+
+// Exclusive scan of one value per thread over a 1024-thread block.  scratch = 33 uint32.
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *scratch, uint32_t *total_out) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t incl = warp_inclusive_scan(v, lane);
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = scratch[lane];
+        const uint32_t wi = warp_inclusive_scan(w, lane);
+        scratch[lane] = wi - w;
+        if (lane == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t r = scratch[warp] + incl - v;
+    if (total_out) *total_out = scratch[32];
+    __syncthreads(); // scratch may be reused
+    return r;
+}
+
+// Start of a sort: default digit positions, flags down.
+__global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1) {
+    grid_dependency_wait();
+    if (threadIdx.x == 0) {
+        plan->shift[0] = shift0;
+        plan->shift[1] = shift1;
+        plan->fallback = 0;
+        plan->recount = 0;
+        plan->key_or = 0;
+        plan->max_sub = 0;
+    }
+}
+
+// After the first histogram: put the two partition digits directly under the highest set key bit.
+__global__ void msd_window_kernel(MsdPlan *plan) {
+    grid_dependency_wait();
+    if (threadIdx.x == 0) {
+        const uint32_t key_or = plan->key_or;
+        if (key_or != 0) {
+            const uint32_t top = 31u - (uint32_t) __clz((int) key_or);
+            const uint32_t s1 = top >= 15u ? top - 7u : 8u;
+            if (s1 != plan->shift[0]) {
+                plan->shift[0] = s1;
+                plan->shift[1] = s1 - 8u;
+                plan->recount = 1;
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// Pieces = segments cut at bucket boundaries.  One CTA; B <= 256 buckets, G <= 1024 segments.
+//   bucket_start[b] (b = 1..B-1; entry 0 is taken as 0 and entry B as n; may be NULL when B == 1)
+//   segment g = keys [g*seg_keys, (g+1)*seg_keys) of the array
+// Output, all in position order: pieces[i] = (lo, hi, bucket, segment); seg_first[g] / bucket_first[b]
+// = index of the first piece of segment g / bucket b (G+1 / B+1 entries).  sub_start (may be NULL):
+// the B*256 + 1 starts of the (bucket, digit) runs the pass will produce -- this kernel fills the
+// entries of EMPTY buckets and the end marker; the scatter fills the rest.
+// =====================================================================================
+__global__ void __launch_bounds__(MSD_PLAN_THREADS)
+msd_plan_pieces_kernel(const uint32_t *__restrict__ bucket_start, uint32_t B, uint32_t n, uint32_t seg_keys, uint32_t G,
+                       uint4 *__restrict__ pieces, uint32_t *__restrict__ seg_first, uint32_t *__restrict__ bucket_first,
+                       uint32_t *__restrict__ num_pieces_out, uint32_t *__restrict__ sub_start) {
+    __shared__ uint32_t bs[RADIX + 1];
+    __shared__ uint32_t ne[RADIX + 1]; // ne[b] = number of non-empty buckets among [0, b)
+    __shared__ uint32_t scratch[33];
+    const uint32_t tid = threadIdx.x;
+    grid_dependency_wait();
+    if (tid <= B) bs[tid] = tid == B ? n : (tid == 0 ? 0u : bucket_start[tid]);
+    __syncthreads();
+    const uint32_t nonempty = (tid < B && bs[tid + 1] > bs[tid]) ? 1u : 0u;
+    const uint32_t ne_excl = block_exclusive_scan_1024(nonempty, scratch, nullptr);
+    if (tid <= B) ne[tid] = ne_excl;
+    __syncthreads();
+
+    // first index i in [0, B] with bs[i] > x;  bs[0] = 0 <= x < n = bs[B]  =>  1 <= i <= B
+    auto upper_bound = [&](uint32_t x) {
+        uint32_t lo = 0, hi = B;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (bs[mid] > x) hi = mid;
+            else lo = mid + 1;
+        }
+        return lo;
+    };
+    uint32_t c = 0, b_lo = 0, b_hi = 0, seg_lo = 0, seg_hi = 0;
+    if (tid < G) {
+        const uint64_t lo64 = (uint64_t) tid * seg_keys, hi64 = lo64 + seg_keys;
+        seg_lo = lo64 < n ? (uint32_t) lo64 : n;
+        seg_hi = hi64 < n ? (uint32_t) hi64 : n;
+        if (seg_lo < seg_hi) {
+            b_lo = upper_bound(seg_lo) - 1;     // the bucket holding the segment's first key
+            b_hi = upper_bound(seg_hi - 1) - 1; // ... and its last key
+            c = ne[b_hi + 1] - ne[b_lo];
+        }
+    }
+    uint32_t total = 0;
+    const uint32_t first = block_exclusive_scan_1024(c, scratch, &total);
+    if (tid < G) seg_first[tid] = first;
+    if (tid == 0) {
+        seg_first[G] = total;
+        *num_pieces_out = total;
+    }
+    if (c > 0) {
+        uint32_t i = first;
+        for (uint32_t b = b_lo; b <= b_hi; ++b) {
+            if (bs[b + 1] > bs[b]) {
+                const uint32_t lo = bs[b] > seg_lo ? bs[b] : seg_lo, hi = bs[b + 1] < seg_hi ? bs[b + 1] : seg_hi;
+                pieces[i++] = make_uint4(lo, hi, b, tid);
+            }
+        }
+    }
+    __syncthreads(); // the pieces (global memory) are visible to the whole CTA
+    for (uint32_t i = tid; i < total; i += MSD_PLAN_THREADS) {
+        const uint32_t pb = pieces[i].z;
+        const int prev = i > 0 ? (int) pieces[i - 1].z : -1;
+        for (int b = prev + 1; b <= (int) pb; ++b) bucket_first[b] = i;
+        if (i == total - 1)
+            for (uint32_t b = pb + 1; b <= B; ++b) bucket_first[b] = total;
+    }
+    if (total == 0 && tid <= B) bucket_first[tid] = 0;
+    if (sub_start) {
+        for (uint32_t idx = tid; idx < B * RADIX; idx += MSD_PLAN_THREADS) {
+            const uint32_t b = idx >> RADIX_BITS;
+            if (bs[b + 1] == bs[b]) sub_start[idx] = bs[b];
+        }
+        if (tid == 0) sub_start[B * RADIX] = n;
+    }
+}
+
+// =====================================================================================
+// hist[q][d] = #{keys of piece q whose digit is d}  (multi_radixsort_histograms.comp:31-56 with the
+// work group's slab replaced by the piece).  One CTA per piece; 128-bit streaming loads; lane-private
+// counter columns (bank == lane).  WITH_OR: also folds the OR of all keys into the plan.
+// gate (may be NULL): the kernel only works if *gate != 0.
+// =====================================================================================
+template <bool WITH_OR>
+__global__ void __launch_bounds__(MSD_HIST_THREADS)
+msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__restrict__ pieces,
+                           const uint32_t *__restrict__ num_pieces, MsdPlan *plan, int pass, uint32_t *__restrict__ hist,
+                           const uint32_t *__restrict__ gate) {
+    __shared__ uint32_t cnt[RADIX * 32];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < RADIX * 32; i += MSD_HIST_THREADS) cnt[i] = 0;
+    grid_dependency_wait();
+    if (gate && *gate == 0) return;
+    if (blockIdx.x >= *num_pieces) return;
+    const uint4 pc = pieces[blockIdx.x];
+    const uint32_t shift = plan->shift[pass];
+    __syncthreads();
+    uint32_t *my_col = cnt + lane;
+    uint32_t acc_or = 0;
+    auto count_key = [&](uint32_t k) {
+        atomicAdd(my_col + msd_digit(k, shift) * 32, 1u);
+        if (WITH_OR) acc_or |= k;
+    };
+    {
+        const uint32_t *base = keys + pc.x;
+        const uint32_t cnt_keys = pc.y - pc.x;
+        uint32_t head = (uint32_t) (((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) / sizeof(uint32_t));
+        if (head > cnt_keys) head = cnt_keys;
+        const uint32_t nvec = (cnt_keys - head) / 4;
+        if ((uint32_t) tid < head) count_key(base[tid]);
+        const uint4 *vbase = reinterpret_cast<const uint4 *>(base + head);
+        uint32_t v = tid;
+        for (; v + 3 * MSD_HIST_THREADS < nvec; v += 4 * MSD_HIST_THREADS) { // four 128-bit loads in flight
+            uint4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = ld_stream(vbase + v + u * MSD_HIST_THREADS);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                count_key(a[u].x); count_key(a[u].y); count_key(a[u].z); count_key(a[u].w);
+            }
+        }
+        for (; v < nvec; v += MSD_HIST_THREADS) {
+            const uint4 a = ld_stream(vbase + v);
+            count_key(a.x); count_key(a.y); count_key(a.z); count_key(a.w);
+        }
+        const uint32_t tail0 = head + nvec * 4;
+        if (tail0 + tid < cnt_keys) count_key(base[tail0 + tid]);
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        const uint32_t *row = &cnt[tid * 32];
+        uint32_t total = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) total += row[(j + tid) & 31]; // skewed: conflict-free
+        hist[(size_t) blockIdx.x * RADIX + tid] = total;
+    }
+    if (WITH_OR) {
+        acc_or = __reduce_or_sync(0xffffffffu, acc_or);
+        if (lane == 0 && acc_or != 0) atomicOr(&plan->key_or, acc_or);
+    }
+}
+
+// =====================================================================================
+// The unstable scatter.  Persistent CTA: GROUPS worker groups of WORKERS threads + one producer warp;
+// group g of CTA c owns segment c*GROUPS + g and walks its pieces tile by tile:
+//   producer   1-D TMA bulk copies (cp.async.bulk) of whole 16-byte aligned tiles into a two-slot
+//              ring, completion on an mbarrier; a tile may reach past the piece (the keys outside
+//              [lo, hi) are simply not looked at)
+//   rank       r = atomicAdd(cnt[digit], 1): the key's place among the tile's keys of that digit
+//              (this replaces the bin_flags bit matrix + popcounts of multi_radixsort.comp:97-118)
+//   digit thr. tile-local exclusive scan of the 256 counts; the tile's global digit bases from running
+//              per-digit offsets kept in registers (global_offsets[], multi_radixsort.comp:75-76,120-122);
+//              at the first tile of a piece the offsets are rebuilt from the histogram rows of the
+//              piece's bucket (the prologue, multi_radixsort.comp:56-77)
+//   place      key -> sorted[excl[digit] + r] in shared memory
+//   write-out  in tile order: a warp stores 128 B of consecutive positions; the write-out of tile j-1
+//              overlaps the digit threads' work on tile j.
+// UNIFORM_FAST: a round whose 32 keys share one digit (sorted or constant input) is ranked with one
+// atomic by lane 0 instead of 32 serialised ones.
+// =====================================================================================
+template <int WORKERS, int KPT>
+struct MsdGroupSmem {
+    static constexpr int TILE = WORKERS * KPT;
+    alignas(128) uint32_t in[2][TILE];  // TMA destinations
+    alignas(128) uint32_t sorted[TILE]; // tile in digit order, staged for the write-out
+    uint32_t cnt[2][RADIX];             // digit counters of tile j (slot j & 1), then the digits' exclusive bases
+    uint32_t bin_dst[2][RADIX];         // global start of the digit run minus its start in the tile
+    uint32_t scan_scratch[8];
+    alignas(8) uint64_t full[2], empty[2];
+};
+
+template <int WORKERS, int KPT, int GROUPS>
+struct MsdSmem {
+    using Group = MsdGroupSmem<WORKERS, KPT>;
+    Group g[GROUPS];
+};
+
+template <int WORKERS, int KPT, int GROUPS, bool UNIFORM_FAST>
+__global__ void __launch_bounds__(GROUPS * WORKERS + 32, 1)
+msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out, uint32_t n, MsdPlan *plan, int pass,
+                   const uint4 *__restrict__ pieces, const uint32_t *__restrict__ seg_first,
+                   const uint32_t *__restrict__ bucket_first, const uint32_t *__restrict__ bucket_start,
+                   const uint32_t *__restrict__ hist, uint32_t *__restrict__ sub_start, uint32_t max_sub) {
+    using Smem = MsdSmem<WORKERS, KPT, GROUPS>;
+    using Group = typename Smem::Group;
+    constexpr uint32_t TILE = Group::TILE;
+    constexpr int WARPS = WORKERS / 32;
+    constexpr int ALL_WORKERS = GROUPS * WORKERS;
+    static_assert(WORKERS >= RADIX && WORKERS % 32 == 0, "one worker thread per digit is required");
+    extern __shared__ __align__(128) unsigned char smem_raw_msd[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw_msd);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool tma_ok = (reinterpret_cast<uintptr_t>(keys_in) & 15) == 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                mbar_init(&sm.g[gi].full[b], 1);
+                mbar_init(&sm.g[gi].empty[b], WARPS);
+            }
+        mbar_fence_init();
+    }
+    if (tid < ALL_WORKERS) { // counters of the first tile (slot 0) start at zero
+        const int grp0 = tid / WORKERS, g0 = tid - grp0 * WORKERS;
+        if (g0 < RADIX) sm.g[grp0].cnt[0][g0] = 0;
+    }
+    grid_dependency_wait(); // plan, pieces, histogram rows and keys come from earlier kernels
+    __syncthreads();
+
+    // a tile goes through TMA when it is 16-byte aligned in global memory and lies inside the array
+    auto tile_is_tma = [&](uint32_t tb) { return tma_ok && (uint64_t) tb + TILE <= (uint64_t) n; };
+
+    if (tid >= ALL_WORKERS) {
+        // ============================ producer warp (lane 0) ============================
+        if (lane != 0) return;
+        uint32_t q[GROUPS], q_end[GROUPS], t[GROUPS], nt[GROUPS], t0[GROUPS], jj[GROUPS];
+#pragma unroll
+        for (int gi = 0; gi < GROUPS; ++gi) {
+            const uint32_t seg = blockIdx.x * GROUPS + gi;
+            q[gi] = seg_first[seg];
+            q_end[gi] = seg_first[seg + 1];
+            t[gi] = nt[gi] = t0[gi] = jj[gi] = 0;
+        }
+        bool any = true;
+        while (any) {
+            any = false;
+#pragma unroll
+            for (int gi = 0; gi < GROUPS; ++gi) {
+                if (t[gi] == nt[gi]) { // next piece of this group's segment
+                    if (q[gi] == q_end[gi]) continue;
+                    const uint4 pc = pieces[q[gi]++];
+                    t0[gi] = pc.x & ~3u;
+                    nt[gi] = (pc.y - t0[gi] + TILE - 1) / TILE;
+                    t[gi] = 0;
+                }
+                any = true;
+                Group &s = sm.g[gi];
+                const uint32_t slot = jj[gi] & 1, tb = t0[gi] + t[gi] * TILE;
+                if (jj[gi] >= 2) mbar_wait_sleep(&s.empty[slot], ((jj[gi] - 2) >> 1) & 1, 64); // tile jj-2 fully consumed
+                if (tile_is_tma(tb)) {
+                    constexpr uint32_t kbytes = TILE * sizeof(uint32_t);
+                    mbar_arrive_expect_tx(&s.full[slot], kbytes);
+                    bulk_copy_g2s(s.in[slot], keys_in + tb, kbytes, &s.full[slot]);
+                } else {
+                    mbar_arrive(&s.full[slot]); // the workers copy this tile in themselves
+                }
+                ++t[gi];
+                ++jj[gi];
+            }
+        }
+        return;
+    }
+
+    // ==================================== workers ====================================
+    const int grp = GROUPS == 1 ? 0 : tid / WORKERS;
+    const int gtid = tid - grp * WORKERS, warp = gtid >> 5;
+    Group &s = sm.g[grp];
+    const uint32_t seg = blockIdx.x * GROUPS + grp;
+    const uint32_t bar_w = 1 + grp, bar_d = 1 + GROUPS + grp; // this group's worker / digit named barriers
+    const uint32_t shift = plan->shift[pass];
+    const uint32_t chunk0 = warp * (KPT * 32) + lane; // warp-striped: lane l reads chunk[i*32 + l]
+    const bool is_digit_thread = gtid < RADIX;
+    const uint32_t dgt = gtid, dwarp = dgt >> 5;
+    const uint32_t q_begin = seg_first[seg], q_end = seg_first[seg + 1];
+
+    uint32_t running_base = 0; // digit thread: where the next tile's run of its digit starts
+
+    auto write_out = [&](uint32_t pslot, uint32_t count) {
+#pragma unroll
+        for (int k = 0; k < KPT; ++k) {
+            const uint32_t p = gtid + k * WORKERS;
+            if (p < count) {
+                const uint32_t key = s.sorted[p];
+                keys_out[s.bin_dst[pslot][msd_digit(key, shift)] + p] = key;
+            }
+        }
+    };
+
+    uint32_t jj = 0, prev_count = 0;
+    for (uint32_t q = q_begin; q < q_end; ++q) {
+        const uint4 pc = pieces[q]; // (lo, hi, bucket, segment)
+        const uint32_t t0 = pc.x & ~3u;
+        const uint32_t nt = (pc.y - t0 + TILE - 1) / TILE;
+        for (uint32_t t = 0; t < nt; ++t, ++jj) {
+            const uint32_t slot = jj & 1, par = (jj >> 1) & 1;
+            const uint32_t tb = t0 + t * TILE;
+            const uint32_t vlo = (pc.x > tb ? pc.x : tb) - tb;
+            const uint32_t vhi = (pc.y < tb + TILE ? pc.y : tb + TILE) - tb;
+            const uint32_t vcount = vhi - vlo; // keys of the piece inside this tile: positions [vlo, vhi)
+            const bool full = vcount == TILE;
+            const uint32_t *tin = s.in[slot];
+            uint32_t *cnt = s.cnt[slot];
+            mbar_wait(&s.full[slot], par);
+            if (!tile_is_tma(tb)) {
+                for (uint32_t p = gtid; p < TILE; p += WORKERS)
+                    if (p - vlo < vcount) s.in[slot][p] = ld_stream(keys_in + tb + p);
+                named_bar_sync(bar_w, WORKERS);
+            }
+
+            // ---- rank: one shared-memory atomic per key ----
+            uint32_t rk[KPT];
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < KPT; ++i) {
+                    const uint32_t d = msd_digit(tin[chunk0 + i * 32], shift);
+                    if (UNIFORM_FAST) {
+                        const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
+                        if (__all_sync(0xffffffffu, d == d_first)) {
+                            uint32_t b = 0;
+                            if (lane == 0) b = atomicAdd(&cnt[d], 32u);
+                            rk[i] = __shfl_sync(0xffffffffu, b, 0) + lane;
+                        } else {
+                            rk[i] = atomicAdd(&cnt[d], 1u);
+                        }
+                    } else {
+                        rk[i] = atomicAdd(&cnt[d], 1u);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KPT; ++i) {
+                    const uint32_t idx = chunk0 + i * 32;
+                    rk[i] = 0;
+                    if (idx - vlo < vcount) rk[i] = atomicAdd(&cnt[msd_digit(tin[idx], shift)], 1u);
+                }
+            }
+            named_bar_sync(bar_w, WORKERS); // (A) counts of tile jj final; sorted[] holds tile jj-1 completely
+
+            // ---- digit threads: tile-local scan, this tile's global digit bases ----
+            if (is_digit_thread) {
+                const uint32_t total = cnt[dgt];
+                const uint32_t incl = warp_inclusive_scan(total, lane);
+                if (lane == 31) s.scan_scratch[dwarp] = incl;
+                named_bar_sync(bar_d, RADIX);
+                uint32_t warp_prefix = 0;
+#pragma unroll
+                for (int w = 0; w < RADIX / 32; ++w)
+                    if (w < (int) dwarp) warp_prefix += s.scan_scratch[w];
+                const uint32_t local_excl = warp_prefix + incl - total;
+                cnt[dgt] = local_excl;        // place() adds the key's rank to this
+                s.cnt[slot ^ 1][dgt] = 0;     // counters of tile jj+1 (its last readers passed barrier A)
+                if (t == 0) {
+                    // prologue of the piece (multi_radixsort.comp:56-77 over the rows of ONE bucket):
+                    // first output index of this piece's keys with digit dgt
+                    const uint32_t b = pc.z;
+                    const uint32_t qf = bucket_first[b], ql = bucket_first[b + 1];
+                    uint32_t below = 0, btotal = 0;
+                    uint32_t q2 = qf;
+                    for (; q2 + 8 <= ql; q2 += 8) { // eight independent loads in flight
+                        uint32_t hh[8];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) hh[u] = __ldcg(hist + (size_t) (q2 + u) * RADIX + dgt);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            btotal += hh[u];
+                            if (q2 + u < q) below += hh[u];
+                        }
+                    }
+                    for (; q2 < ql; ++q2) {
+                        const uint32_t hh = __ldcg(hist + (size_t) q2 * RADIX + dgt);
+                        btotal += hh;
+                        if (q2 < q) below += hh;
+                    }
+                    named_bar_sync(bar_d, RADIX); // everyone has read the tile scan's scratch
+                    const uint32_t bincl = warp_inclusive_scan(btotal, lane);
+                    if (lane == 31) s.scan_scratch[dwarp] = bincl;
+                    named_bar_sync(bar_d, RADIX);
+                    uint32_t bprefix = 0;
+#pragma unroll
+                    for (int w = 0; w < RADIX / 32; ++w)
+                        if (w < (int) dwarp) bprefix += s.scan_scratch[w];
+                    const uint32_t run_start = (bucket_start && b > 0 ? bucket_start[b] : 0u) + bprefix + bincl - btotal;
+                    running_base = run_start + below;
+                    if (sub_start && q == qf) { // the bucket's first piece publishes the run starts
+                        sub_start[b * RADIX + dgt] = run_start;
+                        if (max_sub) {
+                            if (btotal > max_sub && shift > 0) plan->fallback = 1;
+                            const uint32_t wmax = __reduce_max_sync(0xffffffffu, btotal);
+                            if (lane == 0 && wmax > LOCAL_MAX / 2) atomicMax(&plan->max_sub, wmax);
+                        }
+                    }
+                }
+                s.bin_dst[slot][dgt] = running_base - local_excl;
+                running_base += total;
+            }
+            // ---- write tile jj-1 out (overlaps the digit threads' work above) ----
+            if (jj > 0) write_out(slot ^ 1, prev_count);
+            named_bar_sync(bar_w, WORKERS); // (B) digit bases and bin_dst of tile jj ready; sorted[] free
+
+            // ---- keys of tile jj to their place in the staging buffer ----
+            if (full) {
+#pragma unroll
+                for (int i = 0; i < KPT; ++i) {
+                    const uint32_t key = tin[chunk0 + i * 32];
+                    s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < KPT; ++i) {
+                    const uint32_t idx = chunk0 + i * 32;
+                    if (idx - vlo < vcount) {
+                        const uint32_t key = tin[idx];
+                        s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s.empty[slot]); // ring slot may be refilled
+            prev_count = vcount;
+        }
+    }
+    if (jj > 0) { // drain: the last tile of the segment
+        named_bar_sync(bar_w, WORKERS);
+        write_out((jj - 1) & 1, prev_count);
+    }
+}
+
+// =====================================================================================
+// Local sort: CTA c takes the (digit1, digit2) buckets c, c + gridDim.x, ... ; a bucket [lo, hi) of
+// buf0 holds at most LOCAL_MAX keys that agree in every bit above the low 16 and is sorted by its
+// low 16 bits in shared memory, in place:
+//   byte 0   unstable (one atomic per key), keys held in registers
+//   byte 1   stable: the warp-private ballot ranking of the digit pass (vkrs_tile.cuh /
+//            multi_radixsort.comp:97-122), skipped when 8 or fewer low bits are left.
+// =====================================================================================
+struct LocalSmem {
+    uint32_t a[LOCAL_MAX];
+    uint32_t b[LOCAL_MAX];
+    uint32_t warp_cnt[LOCAL_THREADS / 32][RADIX];
+    uint32_t cnt[RADIX];
+    uint32_t scratch[8];
+};
+
+__global__ void __launch_bounds__(LOCAL_THREADS, 4)
+msd_local_sort_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start, uint32_t num_sub,
+                      const MsdPlan *__restrict__ plan) {
+    extern __shared__ __align__(128) unsigned char smem_raw_local[];
+    LocalSmem &sm = *reinterpret_cast<LocalSmem *>(smem_raw_local);
+    constexpr int WARPS = LOCAL_THREADS / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    grid_dependency_wait();
+    if (plan->fallback != 0) return;
+    const uint32_t low_bits = plan->shift[1];
+    if (low_bits == 0) return;
+    const bool two_bytes = low_bits > 8;
+    const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
+    const DigitBitMasks bm(8);
+    const LaneNibbleConsts lc(lane);
+    uint32_t *my_cnt = sm.warp_cnt[warp];
+
+    for (uint32_t j = blockIdx.x; j < num_sub; j += gridDim.x) {
+        const uint32_t lo = __ldcg(sub_start + j), hi = __ldcg(sub_start + j + 1);
+        const uint32_t cnt_keys = hi - lo;
+        if (cnt_keys <= 1 || cnt_keys > LOCAL_MAX) continue; // (> LOCAL_MAX cannot happen without the fallback flag)
+        const uint32_t rounds = (cnt_keys + LOCAL_THREADS - 1) / LOCAL_THREADS;
+        uint32_t *gk = keys + lo;
+
+        // ---- byte 0: load, count + rank with one atomic, scan, place into b[] ----
+        uint32_t key[LOCAL_KPT], rk2[LOCAL_KPT / 2]; // ranks < LOCAL_MAX: two per register
+        auto set_rank = [&](int i, uint32_t r) {
+            if (i & 1) rk2[i / 2] |= r << 16;
+            else rk2[i / 2] = r;
+        };
+        auto get_rank = [&](int i) { return (i & 1) ? (rk2[i / 2] >> 16) : (rk2[i / 2] & 0xffffu); };
+        sm.cnt[tid] = 0;
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = tid + i * LOCAL_THREADS;
+                key[i] = p < cnt_keys ? ld_stream(gk + p) : 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = tid + i * LOCAL_THREADS;
+                uint32_t r = 0;
+                if (p < cnt_keys) r = atomicAdd(&sm.cnt[key[i] & 255u], 1u);
+                set_rank(i, r);
+            }
+        }
+        __syncthreads();
+        {
+            const uint32_t total = sm.cnt[tid];
+            const uint32_t excl = block_exclusive_scan_256(total, sm.scratch, nullptr);
+            sm.cnt[tid] = excl;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = tid + i * LOCAL_THREADS;
+                if (p < cnt_keys) sm.b[sm.cnt[key[i] & 255u] + get_rank(i)] = key[i];
+            }
+        }
+        __syncthreads();
+        if (!two_bytes) {
+#pragma unroll
+            for (int i = 0; i < LOCAL_KPT; ++i) {
+                if (i < (int) rounds) {
+                    const uint32_t p = tid + i * LOCAL_THREADS;
+                    if (p < cnt_keys) gk[p] = sm.b[p];
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- byte 1, stable: warp w owns positions [w*rounds*32, (w+1)*rounds*32) of b[] ----
+#pragma unroll
+        for (int c = 0; c < RADIX / 32; ++c) my_cnt[lane + 32 * c] = 0;
+        __syncwarp();
+        const uint32_t p0 = warp * (rounds * 32) + lane;
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = p0 + i * 32;
+                // padding is all-ones: digit 255 and last in order, so it ranks behind every real key
+                const uint32_t k = p < cnt_keys ? sm.b[p] : 0xFFFFFFFFu;
+                const uint32_t d = (k >> 8) & 255u;
+                const uint32_t peers = match_key_table(k, d, bm, lc);
+                const uint32_t r = my_cnt[d] + __popc(peers & lt_mask);
+                if ((peers & gt_mask) == 0) my_cnt[d] = r + 1; // highest lane of the group
+                key[i] = k;
+                set_rank(i, r);
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) total += sm.warp_cnt[w][tid];
+            uint32_t running = block_exclusive_scan_256(total, sm.scratch, nullptr);
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = sm.warp_cnt[w][tid];
+                sm.warp_cnt[w][tid] = running;
+                running += c;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = p0 + i * 32;
+                if (p < cnt_keys) sm.a[my_cnt[(key[i] >> 8) & 255u] + get_rank(i)] = key[i];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < LOCAL_KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = tid + i * LOCAL_THREADS;
+                if (p < cnt_keys) gk[p] = sm.a[p];
+            }
+        }
+        // a[] / b[] / cnt[] are next written behind at least one barrier of the next bucket
+        __syncthreads();
+    }
+}
+
+} // namespace vkrs

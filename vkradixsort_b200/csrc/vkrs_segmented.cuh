@@ -90,7 +90,8 @@ constexpr int SEGHIST_THREADS = 512;
 template <typename KeyT, bool PARTITION, int XF_IN = 0>
 __global__ void __launch_bounds__(SEGHIST_THREADS)
 segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shift, uint32_t key_base,
-                         uint32_t tile_keys, uint32_t num_tiles, uint32_t *__restrict__ hist) {
+                         uint32_t tile_keys, uint32_t num_tiles, uint32_t *__restrict__ hist,
+                         const uint32_t *__restrict__ gate) {
     __shared__ uint32_t cnt[RADIX * 32]; // [digit][lane]: bank == lane, one wavefront per atomic
     const int tid = threadIdx.x, lane = tid & 31;
     uint32_t first, count;
@@ -103,6 +104,7 @@ segment_histogram_kernel(const KeyT *__restrict__ keys, uint32_t n, uint32_t shi
     auto count_key = [&](KeyT k) { atomicAdd(my_col + digit(KeyXform<KeyT, XF_IN>::fwd(k)) * 32, 1u); };
     for (int i = tid; i < RADIX * 32; i += SEGHIST_THREADS) cnt[i] = 0;
     grid_dependency_wait(); // programmatic dependent launch: everything above overlaps the previous kernel's tail
+    if (gate && *gate == 0) return; // conditional pass (fallback of the bucket schedule, vkrs_msd.cuh): not needed
     __syncthreads();
     if (lo < hi) {
         constexpr int VEC = 16 / sizeof(KeyT);
@@ -190,7 +192,8 @@ __global__ void __launch_bounds__(GROUPS * WORKERS + 32, MIN_BLOCKS)
 segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ keys_out,
                          const uint32_t *__restrict__ vals_in, uint32_t *__restrict__ vals_out, uint32_t n,
                          uint32_t shift, uint32_t key_base, const uint32_t *__restrict__ hist, uint32_t num_tiles,
-                         unsigned long long *dbg, const unsigned long long *__restrict__ dst_tables) {
+                         unsigned long long *dbg, const unsigned long long *__restrict__ dst_tables,
+                         const uint32_t *__restrict__ gate) {
     using Smem = SegSmem<KeyT, HAS_VALUES, WORKERS, KPT, GROUPS>;
     using Group = typename Smem::Group;
     constexpr int WARPS = Group::WARPS;
@@ -219,6 +222,7 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
     }
     grid_dependency_wait(); // the histogram matrix and (in later passes) the keys come from earlier kernels
     __syncthreads();
+    if (gate && *gate == 0) return; // conditional pass (fallback of the bucket schedule, vkrs_msd.cuh): not needed
 
     // A tile can go through TMA when it is full and its global address is 16-byte aligned.
     auto tile_is_tma = [&](uint32_t tile) { return tma_ok && (uint64_t) n - (uint64_t) tile * TILE >= TILE; };
