@@ -12,6 +12,8 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvkradixsort_b200.so")
+if os.environ.get("VKRS_LIB_PATH"):  # tuning runs: a differently configured build of the same library
+    LIB_PATH = os.environ["VKRS_LIB_PATH"]
 
 VKRS_OK = 0
 VKRS_ERR_INVALID_ARGUMENT = -1

@@ -102,6 +102,9 @@ struct vkrs_context {
     uint32_t msd_segments_cap = 0; // segments the workspace was laid out for
     uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
     int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
+    uint32_t msd_local_paths = 3; // local sort: bit 0 bitmap path, bit 1 bins path (VKRS_LOCAL_PATHS, tuning / tests)
+    uint32_t *msd_items = nullptr; // item_first[items + 1] | item_lo[items + 1] of the local sort
+    uint64_t msd_items_cap = 0;
 };
 
 namespace {
@@ -423,7 +426,7 @@ int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments,
     if (configured_device != h->device) {
         int r = set_smem(h, kernel, sizeof(MsdScatterSmem));
         if (r) return r;
-        r = set_smem(h, msd_local_sort_kernel, sizeof(LocalSmem));
+        r = set_smem(h, msd_local_tile_kernel, sizeof(LocalTileSmem));
         if (r) return r;
         VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, MSD_GROUPS * MSD_WORKERS + 32, sizeof(MsdScatterSmem)));
         if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "bucket scatter kernel does not fit on an SM");
@@ -556,11 +559,24 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
                                 (const uint32_t *) w.bucket_start, (const uint32_t *) w.hist[1], w.sub_start, (uint32_t) LOCAL_MAX));
     }
     if (h->msd_stop_after == 2) return VKRS_OK;
-    // ---- every (digit1, digit2) bucket sorted in shared memory, in place ----
+    // ---- the (digit1, digit2) buckets, batched into items of whole buckets, sorted in shared memory, in place ----
     {
-        LaunchScope scope(h, "msd_local_sort_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_local_sort_kernel, dim3((unsigned) (h->sm_count * 4)), dim3(LOCAL_THREADS), sizeof(LocalSmem), s, buf0,
-                                (const uint32_t *) w.sub_start, MSD_SUBS, (const MsdPlan *) w.plan));
+        // the item window is picked on the device (lt_window): the table is sized for the smallest one
+        const uint32_t item_stride = (uint32_t) (((uint64_t) n + LT_MIN_WINDOW - 1) / LT_MIN_WINDOW) + 1;
+        r = grow(h, h->msd_items, h->msd_items_cap, 2 * (uint64_t) item_stride, sizeof(uint32_t), false);
+        if (r) return r;
+        uint32_t *item_first = h->msd_items, *item_lo = h->msd_items + item_stride;
+        {
+            LaunchScope scope(h, "msd_items_kernel", s);
+            VKRS_CUDA(h, launch_pdl(msd_items_kernel, dim3(MSD_SUBS / 256), dim3(256), 0, s, (const uint32_t *) w.sub_start, MSD_SUBS, n,
+                                    item_first, item_lo, item_stride, (const MsdPlan *) w.plan));
+        }
+        uint32_t grid = (uint32_t) (h->sm_count * 2);
+        if (grid > item_stride - 1) grid = item_stride - 1;
+        LaunchScope scope(h, "msd_local_tile_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
+                                (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
+                                (const MsdPlan *) w.plan, h->msd_local_paths));
     }
     if (h->msd_stop_after == 3) return VKRS_OK;
     // ---- fallback: four stable LSD passes that only work if some bucket was too large ----
@@ -701,6 +717,7 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         int iv = atoi(v);
         if (iv >= 0 && iv < NUM_VARIANTS) h->variant = iv;
     }
+    if (const char *v = getenv("VKRS_LOCAL_PATHS")) h->msd_local_paths = (uint32_t) atoi(v) & 3u;
     if (const char *v = getenv("VKRS_SCHEDULE")) {
         int iv = atoi(v);
         if (iv >= 0 && iv < VKRS_NUM_SCHEDULES) h->schedule = iv;
@@ -747,6 +764,7 @@ int vkrs_destroy(vkrs_handle h) {
     cudaFree(h->host_buf[0]);
     cudaFree(h->host_buf[1]);
     cudaFree(h->msd_ws);
+    cudaFree(h->msd_items);
     delete h;
     return VKRS_OK;
 }

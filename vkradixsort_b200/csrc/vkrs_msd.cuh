@@ -488,7 +488,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                         if (max_sub) {
                             if (btotal > max_sub && shift > 0) plan->fallback = 1;
                             const uint32_t wmax = __reduce_max_sync(0xffffffffu, btotal);
-                            if (lane == 0 && wmax > LOCAL_MAX / 2) atomicMax(&plan->max_sub, wmax);
+                            if (lane == 0) atomicMax(&plan->max_sub, wmax);
                         }
                     }
                 }
@@ -528,149 +528,449 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 }
 
 // =====================================================================================
-// Local sort: CTA c takes the (digit1, digit2) buckets c, c + gridDim.x, ... ; a bucket [lo, hi) of
-// buf0 holds at most LOCAL_MAX keys that agree in every bit above the low 16 and is sorted by its
-// low 16 bits in shared memory, in place:
-//   byte 0   unstable (one atomic per key), keys held in registers
-//   byte 1   stable: the warp-private ballot ranking of the digit pass (vkrs_tile.cuh /
-//            multi_radixsort.comp:97-122), skipped when 8 or fewer low bits are left.
+// Local sort.  After pass 2 the array is a sequence of 65536 (digit1, digit2) buckets in key order;
+// what is left is to sort every bucket by its low bits.  Buckets are batched into ITEMS: item w = the
+// buckets whose first key lies in window [w*W, (w+1)*W) of the array -- a contiguous range of whole
+// buckets holding fewer than W + (largest bucket) keys.  W is picked on the device from the largest
+// bucket pass 2 saw, so that an item fits the LT_CAP keys of a shared-memory buffer (lt_window()).  An
+// item is sorted by the full key, which is the same thing because its buckets already are in order.
+//
+// msd_local_tile_kernel, one CTA per item at a time; the item's keys were copied into shared memory
+// with cp.async while the previous item was being sorted (three key buffers rotate through the roles
+// "keys", "sorted", "copy target").  Three ways to sort an item, tried in this order:
+//   bitmap   when the item's key span is at most 2^17 values (always, for 10^8 uniform keys): value v is
+//            bit v of a bitmap; a second bit plane takes the second copy of a value.  One atomicOr per
+//            key, a popcount scan over the 4096 words, and a key's final place is
+//            prefix[word] + popc(bits below it) -- exact, nothing to fix up.  A value held three
+//            times or more sends the item to the next path.
+//   bins     an order-preserving map of the key span onto 4096 bins, (key - base) >> s; one atomic to
+//            count, a scan, one atomic to place; then position p ranks its key among the (few) keys of
+//            its bin by comparison.  A bin above LT_BIN_LIMIT keys sends the item on.
+//   buckets  the item's buckets one by one, two 8-bit passes in shared memory (local_bucket_sort): byte 0
+//            unstable with atomics, byte 1 stable with the warp-private ballot ranking of the digit pass
+//            (vkrs_tile.cuh / multi_radixsort.comp:97-122).  Always correct, several times slower.
+// Nothing is written to global memory before a path has succeeded; the sorted item then goes back in
+// place, fully coalesced.
 // =====================================================================================
-struct LocalSmem {
-    uint32_t a[LOCAL_MAX];
-    uint32_t b[LOCAL_MAX];
-    uint32_t warp_cnt[LOCAL_THREADS / 32][RADIX];
-    uint32_t cnt[RADIX];
-    uint32_t scratch[8];
+#ifndef VKRS_LT_CAP
+#define VKRS_LT_CAP 6144
+#endif
+#ifndef VKRS_LT_BIN_BITS
+#define VKRS_LT_BIN_BITS 12
+#endif
+#ifndef VKRS_LT_MIN_BLOCKS
+#define VKRS_LT_MIN_BLOCKS 2
+#endif
+constexpr int LT_THREADS = 512;
+constexpr int LT_CAP = VKRS_LT_CAP; // keys per shared-memory buffer: the largest item the bins path takes
+constexpr int LT_MIN_WINDOW = 256;
+constexpr int LT_BIN_BITS = VKRS_LT_BIN_BITS;
+constexpr int LT_BINS = 1 << LT_BIN_BITS;
+constexpr int LT_BIN_LIMIT = 32;
+constexpr int LT_BPT = LT_BINS / LT_THREADS; // bins per thread in the scan: LT_BPT / 4 conflict-free 128-bit accesses
+constexpr int LT_WORK_WORDS = LT_BINS > (LT_THREADS / 32) * RADIX ? LT_BINS : (LT_THREADS / 32) * RADIX;
+static_assert(LT_BPT % 4 == 0 && LT_BPT >= 4, "whole 128-bit groups of bins per thread");
+static_assert(LT_CAP >= LOCAL_MAX && LT_CAP < 8192, "part sums of the scan are packed two per word below; buffers double as the bucket path's a[] / b[]");
+
+// Window of the item table for a largest bucket of max_sub keys: the largest power of two with
+// window + max_sub <= LT_CAP (an item then fits a buffer), at least LT_MIN_WINDOW.
+__host__ __device__ __forceinline__ uint32_t lt_window(uint32_t max_sub) {
+    uint32_t w = 4096;
+    while (w > (uint32_t) LT_MIN_WINDOW && w + max_sub > (uint32_t) LT_CAP) w >>= 1;
+    return w;
+}
+
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_exclusive_scan_t(uint32_t v, uint32_t *scratch /* 33 */, uint32_t *total_out) {
+    static_assert(THREADS % 32 == 0 && THREADS <= 1024, "whole warps");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t incl = warp_inclusive_scan(v, lane);
+    if (lane == 31) scratch[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = lane < THREADS / 32 ? scratch[lane] : 0u;
+        const uint32_t wi = warp_inclusive_scan(w, lane);
+        scratch[lane] = wi - w;
+        if (lane == 31) scratch[32] = wi;
+    }
+    __syncthreads();
+    const uint32_t r = scratch[warp] + incl - v;
+    if (total_out) *total_out = scratch[32];
+    __syncthreads(); // scratch may be reused
+    return r;
+}
+
+// item_first[w] = first bucket whose start is >= w*window, item_lo[w] = that bucket's start, for
+// w = 0 .. ceil(n / window); the last entry is (num_sub, n).  One thread per bucket.
+__global__ void __launch_bounds__(256)
+msd_items_kernel(const uint32_t *__restrict__ sub_start, uint32_t num_sub, uint32_t n, uint32_t *__restrict__ item_first,
+                 uint32_t *__restrict__ item_lo, uint32_t item_stride, const MsdPlan *__restrict__ plan) {
+    grid_dependency_wait();
+    if (plan->fallback != 0) return;
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= num_sub) return;
+    const uint32_t window = lt_window(plan->max_sub);
+    const uint32_t num_items = (n + window - 1) / window;
+    if (num_items + 1 > item_stride) return; // cannot happen: the table is sized for the smallest window
+    const uint32_t s_j = __ldcg(sub_start + j);
+    const int w_j = (int) (s_j / window);
+    const int w_prev = j > 0 ? (int) (__ldcg(sub_start + j - 1) / window) : -1;
+    const int last = (int) num_items - 1;
+    for (int w = w_prev + 1; w <= w_j && w <= last; ++w) {
+        item_first[w] = j;
+        item_lo[w] = s_j;
+    }
+    if (j == num_sub - 1) {
+        for (int w = w_j + 1; w <= last; ++w) { // windows in which no bucket starts (the tail of a large last bucket)
+            item_first[w] = num_sub;
+            item_lo[w] = n;
+        }
+        item_first[num_items] = num_sub;
+        item_lo[num_items] = n;
+    }
+}
+
+struct LocalTileSmem {
+    // three key buffers that rotate through the roles "this item's keys", "keys in sorted order" and
+    // "cp.async destination of the next item's keys" (+ slack: 16-byte copy groups, neighbour reads)
+    alignas(16) uint32_t buf[3][LT_CAP + 8];
+    // work = work_m + 4.  bins path: bin counters, then running prefixes, work[-1] stays 0; bucket path: warp_cnt[16][256]
+    alignas(16) uint32_t work_m[4 + LT_WORK_WORDS];
+    uint32_t small_cnt[RADIX];                         // bucket path: byte-0 counters
+    uint32_t cand_lo[LT_THREADS], cand_hi[LT_THREADS]; // bucket path: bounds of one chunk of buckets
+    uint32_t scratch[40];
 };
 
-__global__ void __launch_bounds__(LOCAL_THREADS, 4)
-msd_local_sort_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start, uint32_t num_sub,
-                      const MsdPlan *__restrict__ plan) {
-    extern __shared__ __align__(128) unsigned char smem_raw_local[];
-    LocalSmem &sm = *reinterpret_cast<LocalSmem *>(smem_raw_local);
-    constexpr int WARPS = LOCAL_THREADS / 32;
+__device__ __forceinline__ void cp_async_4(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_16(uint32_t *smem_dst, const uint32_t *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Starts the copy of keys [lo, hi) into buf so that key lo + i lands at buf[(lo & 3) + i]: whole 16-byte
+// groups where the array allows it, single keys for the rest.  n = size of the array.  Nothing is
+// copied when the item does not fit a buffer (it is then sorted bucket by bucket from global memory).
+__device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__restrict__ keys, uint32_t lo, uint32_t hi, uint32_t n,
+                                              bool base_aligned) {
+    const uint32_t tid = threadIdx.x;
+    if (hi > lo && hi - lo <= (uint32_t) LT_CAP) {
+        const uint32_t a0 = lo & ~3u;
+        uint32_t a1 = a0; // [a0, a1): 16-byte groups that lie inside the array
+        if (base_aligned) {
+            a1 = (hi + 3u) & ~3u;
+            if (a1 > (n & ~3u)) a1 = n & ~3u;
+            if (a1 < a0) a1 = a0;
+            for (uint32_t g = a0 + 4 * tid; g < a1; g += 4 * LT_THREADS) cp_async_16(&buf[g - a0], keys + g);
+        }
+        for (uint32_t p = (a1 > lo ? a1 : lo) + tid; p < hi; p += LT_THREADS) cp_async_4(&buf[p - a0], keys + p);
+    }
+    cp_async_commit();
+}
+
+// Robust shared-memory sort of one bucket gk[0, cnt_keys), cnt_keys <= LOCAL_MAX, by its low 16 bits
+// (8 if !two_bytes).  All THREADS threads of the CTA call it.  a / b: LOCAL_MAX keys each; warp_cnt:
+// [THREADS/32][256]; small_cnt: 256; scratch: 8.
+template <int THREADS>
+__device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uint32_t cnt_keys, bool two_bytes, uint32_t *a,
+                                                  uint32_t *b, uint32_t *warp_cnt, uint32_t *small_cnt, uint32_t *scratch) {
+    constexpr int WARPS = THREADS / 32;
+    constexpr int KPT = LOCAL_MAX / THREADS;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
+    const DigitBitMasks bm(8);
+    const LaneNibbleConsts lc(lane);
+    uint32_t *my_cnt = warp_cnt + warp * RADIX;
+    const uint32_t rounds = (cnt_keys + THREADS - 1) / THREADS;
+
+    // ---- byte 0: load, count + rank with one atomic, scan, place into b[] ----
+    uint32_t key[KPT], rk2[KPT / 2] = {}; // ranks < LOCAL_MAX: two per register
+    auto set_rank = [&](int i, uint32_t r) {
+        if (i & 1) rk2[i / 2] |= r << 16;
+        else rk2[i / 2] = r;
+    };
+    auto get_rank = [&](int i) { return (i & 1) ? (rk2[i / 2] >> 16) : (rk2[i / 2] & 0xffffu); };
+    if (tid < RADIX) small_cnt[tid] = 0;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = tid + i * THREADS;
+            key[i] = p < cnt_keys ? ld_stream(gk + p) : 0xFFFFFFFFu;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = tid + i * THREADS;
+            uint32_t r = 0;
+            if (p < cnt_keys) r = atomicAdd(&small_cnt[key[i] & 255u], 1u);
+            set_rank(i, r);
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t total = tid < RADIX ? small_cnt[tid] : 0u;
+        const uint32_t excl = block_exclusive_scan_256(total, scratch, nullptr);
+        if (tid < RADIX) small_cnt[tid] = excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = tid + i * THREADS;
+            if (p < cnt_keys) b[small_cnt[key[i] & 255u] + get_rank(i)] = key[i];
+        }
+    }
+    __syncthreads();
+    if (!two_bytes) {
+#pragma unroll
+        for (int i = 0; i < KPT; ++i) {
+            if (i < (int) rounds) {
+                const uint32_t p = tid + i * THREADS;
+                if (p < cnt_keys) gk[p] = b[p];
+            }
+        }
+        __syncthreads();
+        return;
+    }
+
+    // ---- byte 1, stable: warp w owns positions [w*rounds*32, (w+1)*rounds*32) of b[] ----
+#pragma unroll
+    for (int c = 0; c < RADIX / 32; ++c) my_cnt[lane + 32 * c] = 0;
+    __syncwarp();
+    const uint32_t p0 = warp * (rounds * 32) + lane;
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = p0 + i * 32;
+            // padding is all-ones: digit 255 and last in order, so it ranks behind every real key
+            const uint32_t k = p < cnt_keys ? b[p] : 0xFFFFFFFFu;
+            const uint32_t d = (k >> 8) & 255u;
+            const uint32_t peers = match_key_table(k, d, bm, lc);
+            const uint32_t r = my_cnt[d] + __popc(peers & lt_mask);
+            if ((peers & gt_mask) == 0) my_cnt[d] = r + 1; // highest lane of the group
+            key[i] = k;
+            set_rank(i, r);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t total = 0;
+        if (tid < RADIX) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) total += warp_cnt[w * RADIX + tid];
+        }
+        uint32_t running = block_exclusive_scan_256(total, scratch, nullptr);
+        if (tid < RADIX) {
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = warp_cnt[w * RADIX + tid];
+                warp_cnt[w * RADIX + tid] = running;
+                running += c;
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = p0 + i * 32;
+            if (p < cnt_keys) a[my_cnt[(key[i] >> 8) & 255u] + get_rank(i)] = key[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < KPT; ++i) {
+        if (i < (int) rounds) {
+            const uint32_t p = tid + i * THREADS;
+            if (p < cnt_keys) gk[p] = a[p];
+        }
+    }
+    __syncthreads(); // a[] / b[] / counters are free again
+}
+
+// Bins path of one item: keys in `in[0, size)`, (key - base) >> s < LT_BINS; `grouped` is scratch.  Writes the
+// sorted item to gk[0, size) and returns false, or returns true (nothing written) when some bin is over-full.
+__device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_t *in, uint32_t *grouped, uint32_t *__restrict__ gk,
+                                                uint32_t size, uint32_t base, uint32_t s) {
+    const int tid = threadIdx.x;
+    uint32_t *cnt = sm.work_m + 4;
+    uint4 *cv = reinterpret_cast<uint4 *>(cnt);
+    constexpr int PARTS = LT_BPT / 4; // thread t owns bins [4t, 4t+4) of each of PARTS equal parts of the bin range
+#pragma unroll
+    for (int k = 0; k < PARTS; ++k) cv[k * LT_THREADS + tid] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) sm.work_m[3] = 0;
+    __syncthreads();
+
+    // ---- count: one shared-memory reduction per key ----
+#pragma unroll 4
+    for (uint32_t p = tid; p < size; p += LT_THREADS) atomicAdd(&cnt[(in[p] - base) >> s], 1u);
+    __syncthreads();
+
+    // ---- scan: conflict-free 128-bit accesses; the part sums (< 2^13) are scanned two per word ----
+    {
+        static_assert(PARTS == 2 || PARTS == 4, "two or four parts");
+        uint32_t sum[PARTS], maxc = 0;
+#pragma unroll
+        for (int k = 0; k < PARTS; ++k) {
+            const uint4 v = cv[k * LT_THREADS + tid];
+            sum[k] = v.x + v.y + v.z + v.w;
+            maxc = max(max(maxc, max(v.x, v.y)), max(v.z, v.w));
+        }
+        uint32_t run[PARTS];
+        {
+            uint32_t total = 0;
+            const uint32_t ex = block_exclusive_scan_t<LT_THREADS>(sum[0] | (sum[1] << 16), sm.scratch, &total);
+            run[0] = ex & 0xffffu;
+            run[1] = (ex >> 16) + (total & 0xffffu);
+            if (PARTS == 4) {
+                const uint32_t first_half = (total & 0xffffu) + (total >> 16);
+                uint32_t total2 = 0;
+                const uint32_t ex2 = block_exclusive_scan_t<LT_THREADS>(sum[PARTS - 2] | (sum[PARTS - 1] << 16), sm.scratch, &total2);
+                run[PARTS - 2] = first_half + (ex2 & 0xffffu);
+                run[PARTS - 1] = first_half + (ex2 >> 16) + (total2 & 0xffffu);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < PARTS; ++k) { // the counts are read again rather than kept in registers across the scan
+            const uint4 v = cv[k * LT_THREADS + tid];
+            uint4 o;
+            o.x = run[k];
+            o.y = o.x + v.x;
+            o.z = o.y + v.y;
+            o.w = o.z + v.z;
+            cv[k * LT_THREADS + tid] = o;
+        }
+        // equal bins are equal keys when s == 0: nothing to fix up, any bin size is fine
+        if (__syncthreads_or(s > 0 && maxc > (uint32_t) LT_BIN_LIMIT)) return true;
+    }
+
+    // ---- place: a second atomic on the bin's running prefix hands out the positions; afterwards
+    //      cnt[bin] = one past the last position of the bin, cnt[bin - 1] = its first ----
+#pragma unroll 4
+    for (uint32_t p = tid; p < size; p += LT_THREADS) {
+        const uint32_t k = in[p];
+        grouped[atomicAdd(&cnt[(k - base) >> s], 1u)] = k;
+    }
+    __syncthreads();
+    if (s == 0) {
+#pragma unroll 4
+        for (uint32_t p = tid; p < size; p += LT_THREADS) gk[p] = grouped[p];
+        return false;
+    }
+
+    // ---- fix-up, straight to global memory: position p ranks its key among the keys of its bin (its
+    //      first four unconditionally; the key only moves inside its bin, so the stores stay nearly coalesced) ----
+#pragma unroll 2
+    for (uint32_t p = tid; p < size; p += LT_THREADS) {
+        const uint32_t k = grouped[p];
+        const uint32_t bin = (k - base) >> s;
+        const uint32_t lo = cnt[(int) bin - 1], hi = cnt[bin];
+        uint32_t r = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t q = lo + j;
+            const uint32_t o = grouped[q];
+            r += (q < hi && (o < k || (o == k && q < p))) ? 1u : 0u;
+        }
+        for (uint32_t q = lo + 4; q < hi; ++q) {
+            const uint32_t o = grouped[q];
+            r += (o < k || (o == k && q < p)) ? 1u : 0u;
+        }
+        gk[lo + r] = k;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(LT_THREADS, VKRS_LT_MIN_BLOCKS)
+msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start,
+                      const uint32_t *__restrict__ item_first, const uint32_t *__restrict__ item_lo, uint32_t n,
+                      const MsdPlan *__restrict__ plan, uint32_t paths /* bit 1 clear: bucket path only (tests) */) {
+    extern __shared__ __align__(128) unsigned char smem_raw_tile[];
+    LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_tile);
+    const int tid = threadIdx.x;
     grid_dependency_wait();
     if (plan->fallback != 0) return;
     const uint32_t low_bits = plan->shift[1];
     if (low_bits == 0) return;
     const bool two_bytes = low_bits > 8;
-    const uint32_t lt_mask = lanemask_lt(), gt_mask = lanemask_gt();
-    const DigitBitMasks bm(8);
-    const LaneNibbleConsts lc(lane);
-    uint32_t *my_cnt = sm.warp_cnt[warp];
+    const uint32_t window = lt_window(plan->max_sub);
+    const uint32_t num_items = (n + window - 1) / window;
 
-    for (uint32_t j = blockIdx.x; j < num_sub; j += gridDim.x) {
-        const uint32_t lo = __ldcg(sub_start + j), hi = __ldcg(sub_start + j + 1);
-        const uint32_t cnt_keys = hi - lo;
-        if (cnt_keys <= 1 || cnt_keys > LOCAL_MAX) continue; // (> LOCAL_MAX cannot happen without the fallback flag)
-        const uint32_t rounds = (cnt_keys + LOCAL_THREADS - 1) / LOCAL_THREADS;
-        uint32_t *gk = keys + lo;
-
-        // ---- byte 0: load, count + rank with one atomic, scan, place into b[] ----
-        uint32_t key[LOCAL_KPT], rk2[LOCAL_KPT / 2]; // ranks < LOCAL_MAX: two per register
-        auto set_rank = [&](int i, uint32_t r) {
-            if (i & 1) rk2[i / 2] |= r << 16;
-            else rk2[i / 2] = r;
-        };
-        auto get_rank = [&](int i) { return (i & 1) ? (rk2[i / 2] >> 16) : (rk2[i / 2] & 0xffffu); };
-        sm.cnt[tid] = 0;
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = tid + i * LOCAL_THREADS;
-                key[i] = p < cnt_keys ? ld_stream(gk + p) : 0xFFFFFFFFu;
-            }
+    uint32_t w = blockIdx.x;
+    if (w >= num_items) return;
+    // descriptors one item ahead of the keys, keys one item ahead of the sort
+    uint32_t lo = __ldcg(item_lo + w), hi = __ldcg(item_lo + w + 1);
+    uint32_t j0 = __ldcg(item_first + w), j1 = __ldcg(item_first + w + 1);
+    uint32_t b_in = 0, b_sorted = 1, b_next = 2; // roles of the three key buffers
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+    prefetch_item(sm.buf[b_in], keys, lo, hi, n, base_aligned);
+    for (; w < num_items; w += gridDim.x) {
+        const uint32_t wn = w + gridDim.x;
+        uint32_t nlo = 0, nhi = 0, nj0 = 0, nj1 = 0;
+        if (wn < num_items) {
+            nlo = __ldcg(item_lo + wn);
+            nhi = __ldcg(item_lo + wn + 1);
+            nj0 = __ldcg(item_first + wn);
+            nj1 = __ldcg(item_first + wn + 1);
         }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = tid + i * LOCAL_THREADS;
-                uint32_t r = 0;
-                if (p < cnt_keys) r = atomicAdd(&sm.cnt[key[i] & 255u], 1u);
-                set_rank(i, r);
-            }
-        }
-        __syncthreads();
-        {
-            const uint32_t total = sm.cnt[tid];
-            const uint32_t excl = block_exclusive_scan_256(total, sm.scratch, nullptr);
-            sm.cnt[tid] = excl;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = tid + i * LOCAL_THREADS;
-                if (p < cnt_keys) sm.b[sm.cnt[key[i] & 255u] + get_rank(i)] = key[i];
-            }
-        }
-        __syncthreads();
-        if (!two_bytes) {
-#pragma unroll
-            for (int i = 0; i < LOCAL_KPT; ++i) {
-                if (i < (int) rounds) {
-                    const uint32_t p = tid + i * LOCAL_THREADS;
-                    if (p < cnt_keys) gk[p] = sm.b[p];
+        const uint32_t size = hi - lo;
+        cp_async_wait_all();
+        __syncthreads(); // this item's keys are in buf[b_in]; buf[b_next] and the work area are free
+        // ---- start the copy of the next item: it has the whole of this item's sort to land ----
+        prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned);
+        if (size > 1) {
+            bool todo = true;
+            if (size <= (uint32_t) LT_CAP) {
+                // the item's buckets are j0 .. j1-1 and a key of bucket j is (j << low_bits) + its low bits
+                const uint32_t nb = j1 - j0; // >= 1
+                const uint32_t span_bits = low_bits + (nb > 1 ? 32u - (uint32_t) __clz((int) (nb - 1)) : 0u);
+                const uint32_t base = j0 << low_bits;
+                const uint32_t *in = sm.buf[b_in] + (lo & 3u);
+                uint32_t *gk = keys + lo;
+                if (paths & 2u) {
+                    const uint32_t s = span_bits > (uint32_t) LT_BIN_BITS ? span_bits - (uint32_t) LT_BIN_BITS : 0u;
+                    todo = local_tile_bins(sm, in, sm.buf[b_sorted], gk, size, base, s);
                 }
             }
-            __syncthreads();
-            continue;
-        }
-
-        // ---- byte 1, stable: warp w owns positions [w*rounds*32, (w+1)*rounds*32) of b[] ----
-#pragma unroll
-        for (int c = 0; c < RADIX / 32; ++c) my_cnt[lane + 32 * c] = 0;
-        __syncwarp();
-        const uint32_t p0 = warp * (rounds * 32) + lane;
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = p0 + i * 32;
-                // padding is all-ones: digit 255 and last in order, so it ranks behind every real key
-                const uint32_t k = p < cnt_keys ? sm.b[p] : 0xFFFFFFFFu;
-                const uint32_t d = (k >> 8) & 255u;
-                const uint32_t peers = match_key_table(k, d, bm, lc);
-                const uint32_t r = my_cnt[d] + __popc(peers & lt_mask);
-                if ((peers & gt_mask) == 0) my_cnt[d] = r + 1; // highest lane of the group
-                key[i] = k;
-                set_rank(i, r);
-                __syncwarp();
+            if (todo) {
+                // the item's buckets one by one (empty and one-key buckets are skipped in chunks)
+                __syncthreads();
+                for (uint32_t jb = j0; jb < j1; jb += LT_THREADS) {
+                    const uint32_t j = jb + tid;
+                    uint32_t blo = 0, bhi = 0;
+                    if (j < j1) {
+                        blo = __ldcg(sub_start + j);
+                        bhi = __ldcg(sub_start + j + 1);
+                    }
+                    sm.cand_lo[tid] = blo;
+                    sm.cand_hi[tid] = bhi;
+                    if (__syncthreads_or(bhi - blo > 1) == 0) continue;
+                    const uint32_t chunk = j1 - jb < (uint32_t) LT_THREADS ? j1 - jb : (uint32_t) LT_THREADS;
+                    for (uint32_t c = 0; c < chunk; ++c) {
+                        const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
+                        if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
+                            local_bucket_sort<LT_THREADS>(keys + clo, chi - clo, two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
+                                                          sm.small_cnt, sm.scratch);
+                    }
+                    __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
+                }
             }
         }
-        __syncthreads();
-        {
-            uint32_t total = 0;
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) total += sm.warp_cnt[w][tid];
-            uint32_t running = block_exclusive_scan_256(total, sm.scratch, nullptr);
-#pragma unroll
-            for (int w = 0; w < WARPS; ++w) {
-                const uint32_t c = sm.warp_cnt[w][tid];
-                sm.warp_cnt[w][tid] = running;
-                running += c;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = p0 + i * 32;
-                if (p < cnt_keys) sm.a[my_cnt[(key[i] >> 8) & 255u] + get_rank(i)] = key[i];
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < LOCAL_KPT; ++i) {
-            if (i < (int) rounds) {
-                const uint32_t p = tid + i * LOCAL_THREADS;
-                if (p < cnt_keys) gk[p] = sm.a[p];
-            }
-        }
-        // a[] / b[] / cnt[] are next written behind at least one barrier of the next bucket
-        __syncthreads();
+        lo = nlo;
+        hi = nhi;
+        j0 = nj0;
+        j1 = nj1;
+        const uint32_t t = b_in; // rotate: next keys <- prefetched, sorted scratch <- old keys, prefetch target <- old scratch
+        b_in = b_next;
+        b_next = b_sorted;
+        b_sorted = t;
     }
+    cp_async_wait_all();
 }
 
 } // namespace vkrs
