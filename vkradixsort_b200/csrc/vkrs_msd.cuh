@@ -863,23 +863,22 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
         return false;
     }
 
-    // ---- fix-up, straight to global memory: position p ranks its key among the keys of its bin (its
-    //      first four unconditionally; the key only moves inside its bin, so the stores stay nearly coalesced) ----
+    // ---- fix-up, straight to global memory: position p ranks its key among the keys of its bin by
+    //      (key, offset inside the bin); the key only moves inside its bin, so the stores stay nearly coalesced ----
 #pragma unroll 2
     for (uint32_t p = tid; p < size; p += LT_THREADS) {
         const uint32_t k = grouped[p];
         const uint32_t bin = (k - base) >> s;
-        const uint32_t lo = cnt[(int) bin - 1], hi = cnt[bin];
-        uint32_t r = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint32_t q = lo + j;
-            const uint32_t o = grouped[q];
-            r += (q < hi && (o < k || (o == k && q < p))) ? 1u : 0u;
-        }
-        for (uint32_t q = lo + 4; q < hi; ++q) {
-            const uint32_t o = grouped[q];
-            r += (o < k || (o == k && q < p)) ? 1u : 0u;
+        const uint32_t lo = cnt[(int) bin - 1], n = cnt[bin] - lo, d = p - lo;
+        uint32_t r = d;
+        if (n > 1) {
+            const uint32_t *g = grouped + lo;
+            r = 0;
+#pragma unroll 1
+            for (uint32_t j = 0; j < n; ++j) {
+                const uint32_t o = g[j];
+                r += (o < k || (o == k && j < d)) ? 1u : 0u;
+            }
         }
         gk[lo + r] = k;
     }
