@@ -3,7 +3,9 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload keys|pairs]
 
-One "step" = one complete LSD radix sort (4 digit passes) of one batch of synthetic keys.
+One "step" = one complete sort of one batch of synthetic keys through vkrs_multi_sort (keys only: the
+schedule vkrs_multi_sort picks for that N -- at 10^8 keys the bucket schedule: two unstable top-digit
+partition passes + shared-memory sort of the 16-bit-prefix buckets; pairs: four stable LSD digit passes).
 Workload at every N: BASELINE.json configs[1], 10^8 uniform random uint32 keys PER GPU
 ("scaling": "weak").  At N=1 that is exactly the configuration the metric is quoted on; at N>1
 the N x 10^8 keys are sorted GLOBALLY by the bucket exchange of vkradixsort_b200/dist.py
@@ -15,9 +17,11 @@ Printed by rank 0, ONE JSON line:
              stream around each sort, summed over K steps, max over ranks)
   e2e        the same sort through the host-buffer C-ABI call vkrs_multi_sort_host (pinned host
              keys -> H2D -> sort -> D2H), both copies inside the timed region
-  roofline   the dominant kernel (the fused one-sweep digit pass): algorithmic 8 B/key/launch over
-             its CUDA-event duration, against MEASURED_PEAKS.json's copy bandwidth; plus the whole
-             sort under BASELINE.json's 64 B/key formula
+  roofline   the kernel with the largest share of the step: its algorithmic bytes per launch (8 B/key
+             for a scatter or the local sort: one 4 B read + one 4 B write; 4 B/key for a histogram)
+             over its CUDA-event duration, against MEASURED_PEAKS.json's copy bandwidth; every other
+             kernel of the step the same way under roofline.kernels; plus the whole sort under
+             BASELINE.json's 64 B/key formula
   cpu_baseline  single-thread std::sort of the same 10^8 keys on this box (the reference's own CPU
              arm, MultiRadixSort.cpp:141-146), rank 0, N=1 only
 
@@ -42,7 +46,17 @@ import numpy as np  # noqa: E402
 
 N_KEYS = 100_000_000          # BASELINE.json configs[1]
 ALGO_BYTES_PER_KEY_SORT = 64  # BASELINE.json: 16 B/key/pass x 4 passes (keys only); 96 for pairs
-ALGO_BYTES_PER_KEY_PASS = 8   # the fused digit-pass kernel: one 4 B read + one 4 B write per key
+ALGO_BYTES_PER_KEY_PASS = 8   # a scatter kernel / the local sort: one 4 B read + one 4 B write per key
+ALGO_BYTES_PER_KEY_HIST = 4   # a histogram kernel: one 4 B read per key
+
+
+def algo_bytes_per_key(kernel_name: str, pairs: bool) -> int:
+    """Algorithmic HBM bytes per key and launch of one of the library's kernels."""
+    if "histogram" in kernel_name:
+        return ALGO_BYTES_PER_KEY_HIST
+    if "scatter" in kernel_name or "local_tile" in kernel_name or "onesweep" in kernel_name:
+        return ALGO_BYTES_PER_KEY_PASS * (2 if pairs else 1)
+    return 0  # planning kernels: a few KB
 METRIC = "Mkeys/s on 10^8 uint32 (1/2/4/8xB200); achieved HBM GB/s vs peak"
 SEED = 0x5EED0002
 
@@ -202,6 +216,8 @@ def run_b200(args) -> int:
     handle = Handle(local_rank, n)
     if args.variant is not None:
         handle.set_variant(args.variant)
+    if args.schedule is not None:
+        handle.set_schedule(args.schedule)
 
     host_keys = make_keys(n, SEED + rank)
     pristine = torch.from_numpy(host_keys.view(np.int32)).to(dev)
@@ -297,18 +313,27 @@ def run_b200(args) -> int:
         torch.cuda.synchronize()
         prof = handle.profile()
         handle.set_profiling(False)
-        dom = max(prof.items(), key=lambda kv: kv[1]["ms"])
+        reps = max(1, min(steps, 20))
+        big = {k: v for k, v in prof.items() if algo_bytes_per_key(k, pairs) > 0 and v["ms"] / v["launches"] > 0.02}  # gated-off passes take ~5 us
+        dom = max(big.items(), key=lambda kv: kv[1]["ms"])
         total_prof = sum(v["ms"] for v in prof.values())
-        bytes_per_key = ALGO_BYTES_PER_KEY_PASS * (2 if pairs else 1)
+        bytes_per_key = algo_bytes_per_key(dom[0], pairs)
         dom_ms = dom[1]["ms"] / dom[1]["launches"]
         achieved = n * bytes_per_key / (dom_ms * 1e-3) / 1e9
         sort_bytes = (96 if pairs else ALGO_BYTES_PER_KEY_SORT)
+        kernels = {}
+        for k, v in big.items():
+            per_launch = v["ms"] / v["launches"]
+            gbs = n * algo_bytes_per_key(k, pairs) / (per_launch * 1e-3) / 1e9
+            kernels[k] = {"launches_per_sort": v["launches"] / reps, "avg_launch_ms": per_launch, "achieved": gbs, "frac": gbs / peak,
+                          "share_of_step": v["ms"] / total_prof if total_prof else None}
         roofline = {
             "bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": n * bytes_per_key, "avg_launch_ms": dom_ms,
             "share_of_step": dom[1]["ms"] / total_prof if total_prof else None,
-            "kernels_ms_per_sort": {k: v["ms"] / max(1, min(steps, 20)) for k, v in prof.items()},
+            "kernels": kernels,
+            "kernels_ms_per_sort": {k: v["ms"] / reps for k, v in prof.items()},
             "whole_sort": {"formula_bytes_per_key": sort_bytes,
                            "achieved_gbs": n * sort_bytes / (ms_per_step * 1e-3) / 1e9,
                            "frac_of_measured_peak": n * sort_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
@@ -371,9 +396,12 @@ def run_b200(args) -> int:
             "data": "synthetic",
             "config": {**common_config(pairs, world, n), "l2": "inputs (400 MB) larger than L2 (126 MB); input restored by a "
                        "400 MB device copy before every step", "variant": capi.variant_name(handle.variant),
+                       "schedule": capi.schedule_name(handle.schedule),
                        "timing": "CUDA events on the launch stream around each sort, summed; max over ranks"},
             "clocks": clocks, "gpu_launches": int(launches), "verified": bool(verified),
         }
+        if not pairs:
+            line["config"]["bucket_schedule"] = handle.bucket_stats()  # shifts, fallback flag, largest bucket of the last bucket-schedule sort
         if roofline:
             line["roofline"] = roofline
         if e2e:
@@ -395,7 +423,8 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="keys", choices=["keys", "pairs"])
     ap.add_argument("--n", type=int, default=N_KEYS, help="keys per GPU (default: the BASELINE configuration)")
-    ap.add_argument("--variant", type=int, default=None, help="tuning: kernel tile variant")
+    ap.add_argument("--variant", type=int, default=None, help="tuning: kernel tile variant of the stable LSD passes (forces the LSD schedule)")
+    ap.add_argument("--schedule", type=int, default=None, help="tuning: 1 = LSD, 2 = LSD with unstable first pass, 3 = bucket (default: auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

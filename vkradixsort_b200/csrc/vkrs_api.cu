@@ -384,8 +384,12 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
 constexpr int MSD_WORKERS = 384, MSD_KPT = 16, MSD_GROUPS = 2;
 constexpr uint32_t MSD_TILE = MSD_WORKERS * MSD_KPT;
 constexpr uint32_t MSD_SUBS = RADIX * RADIX;          // (digit1, digit2) buckets
-constexpr uint32_t AUTO_MSD_MIN = 48u << 20;          // vkrs_multi_sort, schedule auto: bucket schedule from here
-constexpr uint32_t AUTO_UNSTABLE_FIRST_MIN = 1u << 20; // ... below it: LSD with an unstable first pass from here
+// vkrs_multi_sort, schedule auto (measured crossovers, profiles/r01_schedule_sweep.jsonl): the bucket schedule wins
+// from 4*10^6 keys up; above 2.2*10^8 uniform keys a 16-bit-prefix bucket passes LOCAL_MAX keys and the schedule would
+// fall back, so the LSD passes are chosen directly -- with an unstable first pass from 3.2*10^7 keys up.
+constexpr uint32_t AUTO_BUCKET_MIN = 1u << 22;
+constexpr uint32_t AUTO_BUCKET_MAX = 220000000u;
+constexpr uint32_t AUTO_UNSTABLE_FIRST_MIN = 1u << 25;
 
 // Workspace of the bucket schedule, laid out for `segments` segments.
 struct MsdWorkspace {
@@ -458,6 +462,32 @@ int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments,
     return VKRS_OK;
 }
 
+// One digit pass of the bucket machinery: histogram of every piece, then the unstable scatter.  with_or: the
+// histogram also gathers the OR of all keys; gate: the histogram only works if *gate != 0 (recount);
+// do_count / do_scatter select the halves.
+int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t ctas,
+             uint32_t num_count_ctas, const uint32_t *bucket_start, uint32_t *sub_start, uint32_t max_sub, bool with_or,
+             const uint32_t *gate, bool do_count, bool do_scatter, cudaStream_t s) {
+    const uint4 *pieces = w.pieces[pass];
+    const uint32_t *num_pieces = &w.plan->num_pieces[pass];
+    if (do_count) {
+        LaunchScope scope(h, gate ? "msd_piece_histogram_kernel<recount>" : "msd_piece_histogram_kernel", s);
+        if (with_or)
+            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<true>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
+                                    w.plan, pass, w.hist[pass], gate));
+        else
+            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
+                                    w.plan, pass, w.hist[pass], gate));
+    }
+    if (do_scatter) {
+        LaunchScope scope(h, "msd_scatter_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>, dim3(ctas), dim3(MSD_GROUPS * MSD_WORKERS + 32),
+                                sizeof(MsdScatterSmem), s, in, out, n, w.plan, pass, pieces, (const uint32_t *) w.seg_first[pass],
+                                (const uint32_t *) w.bucket_first[pass], bucket_start, (const uint32_t *) w.hist[pass], sub_start, max_sub));
+    }
+    return VKRS_OK;
+}
+
 // init + (cached per N) the piece table of the first pass: pieces == segments, one bucket [0, n)
 int msd_begin(vkrs_context *h, const MsdWorkspace &w, uint32_t n, uint32_t segments, uint32_t seg_keys, uint32_t shift0,
               uint32_t shift1, cudaStream_t s) {
@@ -485,19 +515,8 @@ int lsd_unstable_first_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1,
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
     r = msd_begin(h, w, n, segments, seg_keys, 0, 0, s);
     if (r) return r;
-    {
-        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
-                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
-                                (const uint32_t *) nullptr));
-    }
-    {
-        LaunchScope scope(h, "msd_scatter_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>, dim3(ctas), dim3(MSD_GROUPS * MSD_WORKERS + 32),
-                                sizeof(MsdScatterSmem), s, (const uint32_t *) buf0, buf1, n, w.plan, 0, (const uint4 *) w.pieces[0],
-                                (const uint32_t *) w.seg_first[0], (const uint32_t *) w.bucket_first[0], (const uint32_t *) nullptr,
-                                (const uint32_t *) w.hist[0], (uint32_t *) nullptr, 0u));
-    }
+    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, false, nullptr, true, true, s);
+    if (r) return r;
     for (int p = 1; p < 4; ++p) {
         uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
         r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s);
@@ -514,31 +533,18 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
     r = msd_begin(h, w, n, segments, seg_keys, 24, 16, s);
     if (r) return r;
-    auto scatter = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>;
-    const dim3 sblock(MSD_GROUPS * MSD_WORKERS + 32);
     // ---- pass 1: top digit, whole array = one bucket ----
-    {
-        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<true>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
-                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
-                                (const uint32_t *) nullptr));
-    }
+    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
+    if (r) return r;
     {
         LaunchScope scope(h, "msd_window_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_window_kernel, dim3(1), dim3(32), 0, s, w.plan));
     }
-    { // only works when the keys have leading zero bits (the digit window moved)
-        LaunchScope scope(h, "msd_piece_histogram_kernel<recount>", s);
-        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf0,
-                                (const uint4 *) w.pieces[0], (const uint32_t *) &w.plan->num_pieces[0], w.plan, 0, w.hist[0],
-                                (const uint32_t *) &w.plan->recount));
-    }
-    {
-        LaunchScope scope(h, "msd_scatter_kernel", s);
-        VKRS_CUDA(h, launch_pdl(scatter, dim3(ctas), sblock, sizeof(MsdScatterSmem), s, (const uint32_t *) buf0, buf1, n, w.plan, 0,
-                                (const uint4 *) w.pieces[0], (const uint32_t *) w.seg_first[0], (const uint32_t *) w.bucket_first[0],
-                                (const uint32_t *) nullptr, (const uint32_t *) w.hist[0], w.bucket_start, 0u));
-    }
+    // the recount only works when the keys have leading zero bits (the digit window moved)
+    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, false, &w.plan->recount, true, false, s);
+    if (r) return r;
+    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, w.bucket_start, 0, false, nullptr, false, true, s);
+    if (r) return r;
     if (h->msd_stop_after == 1) return VKRS_OK;
     // ---- pass 2: second digit inside each of the 256 buckets ----
     {
@@ -546,18 +552,8 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
         VKRS_CUDA(h, launch_pdl(msd_plan_pieces_kernel, dim3(1), dim3(MSD_PLAN_THREADS), 0, s, (const uint32_t *) w.bucket_start, (uint32_t) RADIX,
                                 n, seg_keys, segments, w.pieces[1], w.seg_first[1], w.bucket_first[1], &w.plan->num_pieces[1], w.sub_start));
     }
-    {
-        LaunchScope scope(h, "msd_piece_histogram_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(segments + RADIX), dim3(MSD_HIST_THREADS), 0, s, (const uint32_t *) buf1,
-                                (const uint4 *) w.pieces[1], (const uint32_t *) &w.plan->num_pieces[1], w.plan, 1, w.hist[1],
-                                (const uint32_t *) nullptr));
-    }
-    {
-        LaunchScope scope(h, "msd_scatter_kernel", s);
-        VKRS_CUDA(h, launch_pdl(scatter, dim3(ctas), sblock, sizeof(MsdScatterSmem), s, (const uint32_t *) buf1, buf0, n, w.plan, 1,
-                                (const uint4 *) w.pieces[1], (const uint32_t *) w.seg_first[1], (const uint32_t *) w.bucket_first[1],
-                                (const uint32_t *) w.bucket_start, (const uint32_t *) w.hist[1], w.sub_start, (uint32_t) LOCAL_MAX));
-    }
+    r = msd_pass(h, w, 1, buf1, buf0, n, ctas, segments + RADIX, w.bucket_start, w.sub_start, (uint32_t) LOCAL_MAX, false, nullptr, true, true, s);
+    if (r) return r;
     if (h->msd_stop_after == 2) return VKRS_OK;
     // ---- the (digit1, digit2) buckets, batched into items of whole buckets, sorted in shared memory, in place ----
     {
@@ -974,7 +970,8 @@ int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *his
     int sched = h->schedule;
     if (sched == VKRS_SCHEDULE_AUTO) {
         if (h->variant != DEFAULT_VARIANT) sched = VKRS_SCHEDULE_LSD; // a tuning variant was picked: run exactly that kernel
-        else sched = n >= AUTO_MSD_MIN ? VKRS_SCHEDULE_BUCKET : (n >= AUTO_UNSTABLE_FIRST_MIN ? VKRS_SCHEDULE_LSD_UNSTABLE_FIRST : VKRS_SCHEDULE_LSD);
+        else if (n >= AUTO_BUCKET_MIN && n <= AUTO_BUCKET_MAX) sched = VKRS_SCHEDULE_BUCKET;
+        else sched = n >= AUTO_UNSTABLE_FIRST_MIN ? VKRS_SCHEDULE_LSD_UNSTABLE_FIRST : VKRS_SCHEDULE_LSD;
     }
     if (sched == VKRS_SCHEDULE_BUCKET) return msd_sort_u32(h, buf0, buf1, n, s);
     if (sched == VKRS_SCHEDULE_LSD_UNSTABLE_FIRST) return lsd_unstable_first_sort_u32(h, buf0, buf1, n, s);
