@@ -98,13 +98,16 @@ int vkrs_multi_pass(vkrs_handle handle, const uint32_t *elements_in, uint32_t *e
                     uint32_t *histograms, const vkrs_multi_push_constants *pc, void *stream);
 
 /* ---- whole sort: the timed loop of MultiRadixSort::execute (MultiRadixSort.cpp:49-62) -----
- * Four 8-bit digit passes, buf0 -> buf1 -> buf0 -> buf1 -> buf0.  pc->g_shift is ignored
- * (the loop sets 0,8,16,24, :57-58); g_num_workgroups / g_num_blocks_per_workgroup describe
- * the caller's histogram buffer (capacity g_num_workgroups*256 uint32, may be NULL) and are
- * otherwise only validated: this entry is free to use its own tiling.  Default schedule: per digit
- * one segment histogram kernel + one persistent, TMA-fed scatter kernel (the reference's own two-stage
- * decomposition with 2 x #SMs segments); the single-sweep chained-scan ("Onesweep") schedules are
- * selectable with vkrs_set_variant -- DESIGN.md 4.1 / 4.2. */
+ * Sorts buf0 by 8-bit digits; result in buf0, buf1 is scratch.  pc->g_shift is ignored (the loop sets
+ * 0,8,16,24, :57-58); g_num_workgroups / g_num_blocks_per_workgroup describe the caller's histogram
+ * buffer (capacity g_num_workgroups*256 uint32, may be NULL) and are otherwise only validated: this
+ * entry is free to use its own tiling and schedule (vkrs_set_schedule below).  Default (auto): the
+ * bucket schedule for 4*10^6 .. 2.2*10^8 keys -- two partition passes on the two most significant
+ * digits that rank without stability, then every 16-bit-prefix bucket sorted in shared memory --, else
+ * the literal four stable passes buf0 -> buf1 -> buf0 -> buf1 -> buf0, each one segment histogram
+ * kernel + one persistent, TMA-fed scatter kernel (the reference's own two-stage decomposition with
+ * 2 x #SMs segments).  Same bytes in buf0 either way.  The single-sweep chained-scan ("Onesweep")
+ * variants of the stable pass are selectable with vkrs_set_variant -- DESIGN.md 4.1-4.3. */
 int vkrs_multi_sort(vkrs_handle handle, uint32_t *buf0, uint32_t *buf1, uint32_t *histograms,
                     const vkrs_multi_push_constants *pc, void *stream);
 
@@ -203,8 +206,9 @@ int vkrs_get_variant(vkrs_handle handle);
  *                        leading zero bits), then every 16-bit-prefix bucket is sorted in shared memory.
  *                        Falls back to LSD on the device, without a host round trip, when a bucket is
  *                        larger than 4096 keys (heavily skewed input).  DESIGN.md 4.1.
- *   AUTO                 BUCKET for large N, LSD_UNSTABLE_FIRST for medium N, LSD below (and whenever a
- *                        tuning variant other than the default was selected with vkrs_set_variant).
+ *   AUTO                 by N, from the measured crossovers: BUCKET for 4*10^6 .. 2.2*10^8 keys, LSD below,
+ *                        LSD_UNSTABLE_FIRST above (LSD whenever a tuning variant other than the default was
+ *                        selected with vkrs_set_variant).
  * Key+payload, 64-bit and typed sorts always run stable LSD passes. */
 typedef enum vkrs_schedule {
     VKRS_SCHEDULE_AUTO = 0,

@@ -16,8 +16,9 @@
 //   * a "semaphore" is stream order: execute() enqueues on the context's stream and returns a token;
 //   * errors: every non-zero C-ABI status becomes std::runtime_error, as the reference throws
 //     (ComputePass.h:51-53);
-//   * MultiRadixSortPass::executeSort() is an addition: the whole 4-pass loop in one call, free to use
-//     the library's own tiling (the fast path); execute() is the literal per-pass dispatch pair.
+//   * MultiRadixSortPass::executeSort() is an addition: the whole sort in one call, free to use the
+//     library's own tiling and schedule (the fast path; setSchedule(VKRS_SCHEDULE_LSD) pins the literal
+//     four stable passes); execute() is the literal per-pass dispatch pair.
 // Header-only; link libvkradixsort_b200.so and the CUDA runtime.
 #pragma once
 #include "vkradixsort_b200.h"
@@ -170,6 +171,8 @@ class MultiRadixSortPass : public ComputePass {
                                  &m_pushConstants, nullptr, nullptr, s));
         return ++m_token;
     }
+    // Addition: which schedule executeSort() runs (vkrs_schedule; default VKRS_SCHEDULE_AUTO).
+    void setSchedule(int schedule) { check(vkrs_set_schedule(m_handle, schedule)); }
     // Addition: the whole loop of MultiRadixSort::execute (MultiRadixSort.cpp:56-61) in one call on the
     // buffers bound for the active frame: (1,0) = keys in/out, (1,1) = scratch, (1,2) = histograms.
     Semaphore executeSort() {
