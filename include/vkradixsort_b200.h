@@ -202,8 +202,8 @@ int vkrs_get_variant(vkrs_handle handle);
  *                        MultiRadixSort::execute loop (MultiRadixSort.cpp:56-61).
  *   LSD_UNSTABLE_FIRST   the same, but pass 0 ranks keys with one shared-memory atomic instead of the
  *                        stable ballot match: a first pass has no earlier order to preserve.
- *   BUCKET               two unstable passes on the two most significant digits (below the keys' common
- *                        leading zero bits), then every 16-bit-prefix bucket is sorted in shared memory.
+ *   BUCKET               two unstable passes on the two most significant digits (below the leading bits all
+ *                        keys share), then every 16-bit-prefix bucket is sorted in shared memory.
  *                        Falls back to LSD on the device, without a host round trip, when a bucket is
  *                        larger than 4096 keys (heavily skewed input).  DESIGN.md 4.1.
  *   AUTO                 by N, from the measured crossovers: BUCKET for 4*10^6 .. 2.2*10^8 keys, LSD below,

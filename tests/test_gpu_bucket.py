@@ -127,11 +127,24 @@ def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
 
     n = 300_000
     rng = np.random.default_rng(7)
-    keys = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
+    # four 16-bit-prefix buckets of 75,000 keys each
+    keys = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
     out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
     st = handle.bucket_stats()
-    assert st["fallback"] == 1 and st["max_bucket"] > 4096, st
+    assert st["fallback"] == 1 and st["max_bucket"] > 4096 and st["shift1"] == 24, st
     assert np.array_equal(out, np.sort(keys))
+    # a prefix shared by ALL keys is no sort work: the digit window moves below it, two passes finish the job
+    keys1 = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
+    out1, _ = run_sort(handle, keys1, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["fallback"] == 0 and st["shift1"] == 8 and st["shift2"] == 0, st
+    assert np.array_equal(out1, np.sort(keys1))
+    # one rank's key range after the multi-GPU exchange: top bits constant, the rest uniform
+    keys4 = (np.uint32(0xC0000000) | (oracle.generate_random(n, 9, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32)
+    out4, _ = run_sort(handle, keys4, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["fallback"] == 0 and st["shift1"] == 22 and st["recount"] == 1, st
+    assert np.array_equal(out4, np.sort(keys4))
     # the same keys spread over many prefixes: no fallback
     keys2 = oracle.generate_random(n, 8, 0xFFFFFFFF)
     out2, _ = run_sort(handle, keys2, dev, capi.SCHEDULE_BUCKET)

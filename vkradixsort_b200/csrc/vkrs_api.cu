@@ -381,7 +381,12 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
 }
 
 // ---- the bucket schedule (vkrs_msd.cuh) -------------------------------------------------------
-constexpr int MSD_WORKERS = 384, MSD_KPT = 16, MSD_GROUPS = 2;
+#ifndef VKRS_MSD_WORKERS
+#define VKRS_MSD_WORKERS 384
+#define VKRS_MSD_KPT 16
+#define VKRS_MSD_GROUPS 2
+#endif
+constexpr int MSD_WORKERS = VKRS_MSD_WORKERS, MSD_KPT = VKRS_MSD_KPT, MSD_GROUPS = VKRS_MSD_GROUPS;
 constexpr uint32_t MSD_TILE = MSD_WORKERS * MSD_KPT;
 constexpr uint32_t MSD_SUBS = RADIX * RADIX;          // (digit1, digit2) buckets
 // vkrs_multi_sort, schedule auto (measured crossovers, profiles/r01_schedule_sweep.jsonl): the bucket schedule wins
@@ -867,12 +872,12 @@ const char *vkrs_schedule_name(int schedule) {
 int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (!out8) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "out8 is NULL");
-    static_assert(sizeof(MsdPlan) == 8 * sizeof(uint32_t), "vkrs_bucket_stats copies the plan as 8 words");
+    static_assert(sizeof(MsdPlan) == 9 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
     memset(out8, 0, 8 * sizeof(uint32_t));
     if (!h->msd_ws) return VKRS_OK;
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, sizeof(MsdPlan), cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     VKRS_CUDA(h, cudaStreamSynchronize(s));
     return VKRS_OK;
 }

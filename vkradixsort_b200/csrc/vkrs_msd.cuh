@@ -45,6 +45,7 @@ struct MsdPlan {
     uint32_t key_or;        // OR of all keys (only gathered by the first histogram)
     uint32_t max_sub;       // diagnostic: size of the largest (digit1, digit2) bucket seen
     uint32_t num_pieces[2]; // pieces of pass 1 / 2 (NOT reset per sort: the pass-1 plan is cached per N)
+    uint32_t key_and;       // AND of all keys (gathered with key_or): bits on which all keys agree are no sort work
 };
 
 constexpr int MSD_PLAN_THREADS = 1024;
@@ -83,23 +84,25 @@ __global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1)
         plan->fallback = 0;
         plan->recount = 0;
         plan->key_or = 0;
+        plan->key_and = 0xFFFFFFFFu;
         plan->max_sub = 0;
     }
 }
 
-// After the first histogram: put the two partition digits directly under the highest set key bit.
+// After the first histogram: put the two partition digits directly under the highest bit on which the
+// keys differ (leading bits shared by all keys -- zeros of small keys, the common prefix of one rank's
+// key range after the multi-GPU exchange -- are no sort work).
 __global__ void msd_window_kernel(MsdPlan *plan) {
     grid_dependency_wait();
     if (threadIdx.x == 0) {
-        const uint32_t key_or = plan->key_or;
-        if (key_or != 0) {
-            const uint32_t top = 31u - (uint32_t) __clz((int) key_or);
-            const uint32_t s1 = top >= 15u ? top - 7u : 8u;
-            if (s1 != plan->shift[0]) {
-                plan->shift[0] = s1;
-                plan->shift[1] = s1 - 8u;
-                plan->recount = 1;
-            }
+        const uint32_t varying = plan->key_or & ~plan->key_and;
+        // all keys equal: nothing to sort; one bucket, no low bits left, no fallback
+        const uint32_t top = varying != 0 ? 31u - (uint32_t) __clz((int) varying) : 0u;
+        const uint32_t s1 = top >= 15u ? top - 7u : 8u;
+        if (s1 != plan->shift[0]) {
+            plan->shift[0] = s1;
+            plan->shift[1] = s1 - 8u;
+            plan->recount = 1;
         }
     }
 }
@@ -205,10 +208,13 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
     const uint32_t shift = plan->shift[pass];
     __syncthreads();
     uint32_t *my_col = cnt + lane;
-    uint32_t acc_or = 0;
+    uint32_t acc_or = 0, acc_and = 0xFFFFFFFFu;
     auto count_key = [&](uint32_t k) {
         atomicAdd(my_col + msd_digit(k, shift) * 32, 1u);
-        if (WITH_OR) acc_or |= k;
+        if (WITH_OR) {
+            acc_or |= k;
+            acc_and &= k;
+        }
     };
     {
         const uint32_t *base = keys + pc.x;
@@ -245,7 +251,11 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
     }
     if (WITH_OR) {
         acc_or = __reduce_or_sync(0xffffffffu, acc_or);
-        if (lane == 0 && acc_or != 0) atomicOr(&plan->key_or, acc_or);
+        acc_and = __reduce_and_sync(0xffffffffu, acc_and);
+        if (lane == 0) {
+            if (acc_or != 0) atomicOr(&plan->key_or, acc_or);
+            if (acc_and != 0xFFFFFFFFu) atomicAnd(&plan->key_and, acc_and);
+        }
     }
 }
 
@@ -897,6 +907,8 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     const uint32_t low_bits = plan->shift[1];
     if (low_bits == 0) return;
     const bool two_bytes = low_bits > 8;
+    // the bits above the two partition digits are shared by all keys (msd_window_kernel)
+    const uint32_t common_high = low_bits + 16u >= 32u ? 0u : (plan->key_and & ~((1u << (low_bits + 16u)) - 1u));
     const uint32_t window = lt_window(plan->max_sub);
     const uint32_t num_items = (n + window - 1) / window;
 
@@ -925,10 +937,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         if (size > 1) {
             bool todo = true;
             if (size <= (uint32_t) LT_CAP) {
-                // the item's buckets are j0 .. j1-1 and a key of bucket j is (j << low_bits) + its low bits
+                // the item's buckets are j0 .. j1-1 and a key of bucket j is common_high + (j << low_bits) + its low bits
                 const uint32_t nb = j1 - j0; // >= 1
                 const uint32_t span_bits = low_bits + (nb > 1 ? 32u - (uint32_t) __clz((int) (nb - 1)) : 0u);
-                const uint32_t base = j0 << low_bits;
+                const uint32_t base = common_high | (j0 << low_bits);
                 const uint32_t *in = sm.buf[b_in] + (lo & 3u);
                 uint32_t *gk = keys + lo;
                 if (paths & 2u) {
