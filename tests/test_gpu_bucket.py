@@ -133,6 +133,14 @@ def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
     st = handle.bucket_stats()
     assert st["fallback"] == 1 and st["max_bucket"] > 4096 and st["shift1"] == 24, st
     assert np.array_equal(out, np.sort(keys))
+    # a top-digit bucket above 256 * 4096 keys must overflow: pass 1 notices, pass 2 is not even run
+    # (max_bucket is only gathered by pass 2), the LSD passes sort the untouched input
+    m = 3_000_000
+    keys0 = ((rng.integers(0, 2, m, dtype=np.uint32) * np.uint32(0xFF000000)) | rng.integers(0, 1 << 24, m, dtype=np.uint32)).astype(np.uint32)
+    out0, _ = run_sort(handle, keys0, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["fallback"] == 1 and st["max_bucket"] == 0 and st["shift1"] == 24, st
+    assert np.array_equal(out0, np.sort(keys0))
     # a prefix shared by ALL keys is no sort work: the digit window moves below it, two passes finish the job
     keys1 = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
     out1, _ = run_sort(handle, keys1, dev, capi.SCHEDULE_BUCKET)

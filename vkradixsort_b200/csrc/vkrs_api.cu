@@ -503,7 +503,8 @@ int msd_begin(vkrs_context *h, const MsdWorkspace &w, uint32_t n, uint32_t segme
     if (h->msd_plan_n != n || h->msd_plan_segments != segments || h->msd_plan_seg_keys != seg_keys) {
         LaunchScope scope(h, "msd_plan_pieces_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_plan_pieces_kernel, dim3(1), dim3(MSD_PLAN_THREADS), 0, s, (const uint32_t *) nullptr, 1u, n, seg_keys,
-                                segments, w.pieces[0], w.seg_first[0], w.bucket_first[0], &w.plan->num_pieces[0], (uint32_t *) nullptr));
+                                segments, w.pieces[0], w.seg_first[0], w.bucket_first[0], &w.plan->num_pieces[0], (uint32_t *) nullptr,
+                                (const uint32_t *) nullptr));
         h->msd_plan_n = n;
         h->msd_plan_segments = segments;
         h->msd_plan_seg_keys = seg_keys;
@@ -555,7 +556,8 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
     {
         LaunchScope scope(h, "msd_plan_pieces_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_plan_pieces_kernel, dim3(1), dim3(MSD_PLAN_THREADS), 0, s, (const uint32_t *) w.bucket_start, (uint32_t) RADIX,
-                                n, seg_keys, segments, w.pieces[1], w.seg_first[1], w.bucket_first[1], &w.plan->num_pieces[1], w.sub_start));
+                                n, seg_keys, segments, w.pieces[1], w.seg_first[1], w.bucket_first[1], &w.plan->num_pieces[1], w.sub_start,
+                                (const uint32_t *) &w.plan->skip_pass2));
     }
     r = msd_pass(h, w, 1, buf1, buf0, n, ctas, segments + RADIX, w.bucket_start, w.sub_start, (uint32_t) LOCAL_MAX, false, nullptr, true, true, s);
     if (r) return r;
@@ -872,7 +874,7 @@ const char *vkrs_schedule_name(int schedule) {
 int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (!out8) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "out8 is NULL");
-    static_assert(sizeof(MsdPlan) == 9 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
+    static_assert(sizeof(MsdPlan) == 10 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
     memset(out8, 0, 8 * sizeof(uint32_t));
     if (!h->msd_ws) return VKRS_OK;
     DeviceGuard guard(h->device);

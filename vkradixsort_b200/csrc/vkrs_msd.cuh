@@ -46,6 +46,7 @@ struct MsdPlan {
     uint32_t max_sub;       // diagnostic: size of the largest (digit1, digit2) bucket seen
     uint32_t num_pieces[2]; // pieces of pass 1 / 2 (NOT reset per sort: the pass-1 plan is cached per N)
     uint32_t key_and;       // AND of all keys (gathered with key_or): bits on which all keys agree are no sort work
+    uint32_t skip_pass2;    // != 0: pass 1 already saw a bucket that is bound to overflow the local sort; pass 2 is not run
 };
 
 constexpr int MSD_PLAN_THREADS = 1024;
@@ -86,6 +87,7 @@ __global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1)
         plan->key_or = 0;
         plan->key_and = 0xFFFFFFFFu;
         plan->max_sub = 0;
+        plan->skip_pass2 = 0;
     }
 }
 
@@ -119,12 +121,14 @@ __global__ void msd_window_kernel(MsdPlan *plan) {
 __global__ void __launch_bounds__(MSD_PLAN_THREADS)
 msd_plan_pieces_kernel(const uint32_t *__restrict__ bucket_start, uint32_t B, uint32_t n, uint32_t seg_keys, uint32_t G,
                        uint4 *__restrict__ pieces, uint32_t *__restrict__ seg_first, uint32_t *__restrict__ bucket_first,
-                       uint32_t *__restrict__ num_pieces_out, uint32_t *__restrict__ sub_start) {
+                       uint32_t *__restrict__ num_pieces_out, uint32_t *__restrict__ sub_start,
+                       const uint32_t *__restrict__ skip) {
     __shared__ uint32_t bs[RADIX + 1];
     __shared__ uint32_t ne[RADIX + 1]; // ne[b] = number of non-empty buckets among [0, b)
     __shared__ uint32_t scratch[33];
     const uint32_t tid = threadIdx.x;
     grid_dependency_wait();
+    if (skip && *skip != 0) return;
     if (tid <= B) bs[tid] = tid == B ? n : (tid == 0 ? 0u : bucket_start[tid]);
     __syncthreads();
     const uint32_t nonempty = (tid < B && bs[tid + 1] > bs[tid]) ? 1u : 0u;
@@ -203,6 +207,7 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
     for (int i = tid; i < RADIX * 32; i += MSD_HIST_THREADS) cnt[i] = 0;
     grid_dependency_wait();
     if (gate && *gate == 0) return;
+    if (pass == 1 && plan->skip_pass2 != 0) return;
     if (blockIdx.x >= *num_pieces) return;
     const uint4 pc = pieces[blockIdx.x];
     const uint32_t shift = plan->shift[pass];
@@ -328,6 +333,9 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
     }
     grid_dependency_wait(); // plan, pieces, histogram rows and keys come from earlier kernels
     __syncthreads();
+    // pass 2 is pointless once pass 1 has seen a bucket that must overflow the local sort; the flag is final
+    // before this kernel starts (only pass 1 raises it), so all CTAs agree and buf0 keeps the original keys
+    if (pass == 1 && plan->skip_pass2 != 0) return;
 
     // a tile goes through TMA when it is 16-byte aligned in global memory and lies inside the array
     auto tile_is_tma = [&](uint32_t tb) { return tma_ok && (uint64_t) tb + TILE <= (uint64_t) n; };
@@ -495,6 +503,11 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                     running_base = run_start + below;
                     if (sub_start && q == qf) { // the bucket's first piece publishes the run starts
                         sub_start[b * RADIX + dgt] = run_start;
+                        // pass 1: a top-digit bucket above 256 * LOCAL_MAX keys holds a 16-bit-prefix bucket above LOCAL_MAX
+                        if (pass == 0 && btotal > (uint32_t) (RADIX * LOCAL_MAX) && plan->shift[1] > 0) {
+                            plan->skip_pass2 = 1;
+                            plan->fallback = 1;
+                        }
                         if (max_sub) {
                             if (btotal > max_sub && shift > 0) plan->fallback = 1;
                             const uint32_t wmax = __reduce_max_sync(0xffffffffu, btotal);
