@@ -207,6 +207,8 @@ def run_b200(args) -> int:
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
