@@ -199,6 +199,10 @@ def run_b200(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -207,8 +211,6 @@ def run_b200(args) -> int:
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries exactly one JSON line: NCCL's own banner / debug lines go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     n = args.n
@@ -410,7 +412,7 @@ def run_b200(args) -> int:
             line["e2e"] = e2e
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=json_out, flush=True)
     handle.close()
     if dist is not None:
         dist.destroy_process_group()

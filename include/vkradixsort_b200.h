@@ -220,6 +220,11 @@ typedef enum vkrs_schedule {
 int vkrs_set_schedule(vkrs_handle handle, int schedule);
 int vkrs_get_schedule(vkrs_handle handle);
 const char *vkrs_schedule_name(int schedule);
+/* Hint for the BUCKET schedule: all keys of the following keys-only sorts lie in [lo_key, hi_key] (e.g. one
+ * rank's key range after the multi-GPU exchange).  The schedule finds the bits all keys share by itself and
+ * skips them; with the hint its first histogram is already counted at the right digit position, which saves
+ * one 4 B/key recount.  A wrong hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint. */
+int vkrs_set_key_span_hint(vkrs_handle handle, uint32_t lo_key, uint32_t hi_key);
 /* Control words of the handle's last BUCKET sort, for tests and diagnostics: out8 = {shift of pass 1,
  * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, OR of all
  * keys, largest bucket seen if > 2048, pieces of pass 1, pieces of pass 2}.  Synchronises `stream`. */

@@ -91,8 +91,10 @@ class NumpyOps:
             self._u32(values_out)[:n] = self._u32(values_in)[:n][order]
         return self.torch.from_numpy(np.bincount(bucket, minlength=256).astype(np.int32))
 
-    def local_sort(self, buf0, buf1, n, val0=None, val1=None):
+    def local_sort(self, buf0, buf1, n, val0=None, val1=None, key_span=None):
         k = self._u32(buf0)[:n]
+        if key_span is not None and n:  # the hint handed to the device sort must cover what this rank received
+            assert key_span[0] <= int(k.min()) and int(k.max()) <= key_span[1], (key_span, int(k.min()), int(k.max()))
         order = np.argsort(k, kind="stable")
         if val0 is not None:
             self._u32(val0)[:n] = self._u32(val0)[:n][order]

@@ -164,6 +164,28 @@ def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
     assert np.array_equal(out3, keys3)
 
 
+def test_key_span_hint(handle, dev, oracle):
+    """vkrs_set_key_span_hint: a right hint saves the histogram recount, a wrong one only costs it."""
+    from vkradixsort_b200 import capi
+
+    n = 400_000
+    keys = (np.uint32(0xC0000000) | (oracle.generate_random(n, 11, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32)
+    handle.set_key_span_hint(0xC0000000, 0xFFFFFFFF)
+    out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["shift1"] == 22 and st["recount"] == 0, st
+    assert np.array_equal(out, np.sort(keys))
+    handle.set_key_span_hint(0, 0xFFFF)  # wrong: the keys are far outside
+    out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["shift1"] == 22 and st["recount"] == 1, st
+    assert np.array_equal(out, np.sort(keys))
+    handle.set_key_span_hint()  # none
+    out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+    assert handle.bucket_stats()["recount"] == 1
+    assert np.array_equal(out, np.sort(keys))
+
+
 def test_bucket_workspace_reuse_and_unaligned(handle, dev, oracle):
     """Sizes going up and down on one handle (the pass-1 piece table is cached per N) and key buffers
     that start at a 4-byte, not 16-byte, aligned address (no TMA: the workers copy the tiles in)."""

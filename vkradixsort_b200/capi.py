@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
     "vkrs_set_schedule", "vkrs_get_schedule", "vkrs_schedule_name", "vkrs_bucket_stats",
-    "vkrs_debug_bucket_stop",
+    "vkrs_debug_bucket_stop", "vkrs_set_key_span_hint",
 ]
 
 # vkrs_schedule (include/vkradixsort_b200.h)
@@ -129,6 +129,7 @@ def load() -> ctypes.CDLL:
         "vkrs_schedule_name": (ctypes.c_char_p, [i32]),
         "vkrs_bucket_stats": (i32, [vp, ctypes.POINTER(u32), vp]),
         "vkrs_debug_bucket_stop": (i32, [vp, i32]),
+        "vkrs_set_key_span_hint": (i32, [vp, u32, u32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -323,6 +324,10 @@ class Handle:
         self._check(self._lib.vkrs_bucket_stats(self._h, out, _stream(stream)))
         names = ("shift1", "shift2", "fallback", "recount", "key_or", "max_bucket", "pieces1", "pieces2")
         return dict(zip(names, (int(v) for v in out)))
+
+    def set_key_span_hint(self, lo_key: int = 0, hi_key: int = 0xFFFFFFFF):
+        """All keys of the following keys-only sorts lie in [lo_key, hi_key]; defaults = no hint."""
+        self._check(self._lib.vkrs_set_key_span_hint(self._h, lo_key, hi_key))
 
     def debug_bucket_stop(self, stage: int):
         """Test aid: end the bucket schedule after stage 1 / 2 / 3 (0 = whole schedule)."""

@@ -102,6 +102,7 @@ struct vkrs_context {
     uint32_t msd_segments_cap = 0; // segments the workspace was laid out for
     uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
     int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
+    uint32_t msd_first_shift = 24; // where the first histogram of the bucket schedule counts (vkrs_set_key_span_hint)
     uint32_t msd_local_paths = 3; // local sort: bit 0 bitmap path, bit 1 bins path (VKRS_LOCAL_PATHS, tuning / tests)
     uint32_t *msd_items = nullptr; // item_first[items + 1] | item_lo[items + 1] of the local sort
     uint64_t msd_items_cap = 0;
@@ -537,7 +538,7 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
     int r = msd_prepare(h, n, ctas, segments, seg_keys);
     if (r) return r;
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
-    r = msd_begin(h, w, n, segments, seg_keys, 24, 16, s);
+    r = msd_begin(h, w, n, segments, seg_keys, h->msd_first_shift, h->msd_first_shift - 8, s);
     if (r) return r;
     // ---- pass 1: top digit, whole array = one bucket ----
     r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
@@ -881,6 +882,19 @@ int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     VKRS_CUDA(h, cudaStreamSynchronize(s));
+    return VKRS_OK;
+}
+
+// Hint: the keys of the following keys-only sorts lie in [lo_key, hi_key].  The bucket schedule then counts its
+// first histogram directly below the bits lo_key and hi_key share; a wrong hint only costs the recount the
+// schedule does anyway when the digit window moves.  (0, 0xFFFFFFFF) = no hint.
+int vkrs_set_key_span_hint(vkrs_handle h, uint32_t lo_key, uint32_t hi_key) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (lo_key > hi_key) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "lo_key > hi_key");
+    const uint32_t x = lo_key ^ hi_key;
+    uint32_t top = 0;
+    while (top < 31 && (x >> (top + 1)) != 0) ++top;
+    h->msd_first_shift = top >= 15 ? top - 7 : 8;
     return VKRS_OK;
 }
 

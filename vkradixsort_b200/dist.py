@@ -131,14 +131,19 @@ class DeviceOps:
     def partition_scatter_p2p(self, keys_in, n, key_base, shift, dst_tables, values_in=None):
         self.handle.partition_scatter_p2p(keys_in, n, key_base, shift, dst_tables, values_in)
 
-    def local_sort(self, buf0, buf1, n, val0=None, val1=None):
+    def local_sort(self, buf0, buf1, n, val0=None, val1=None, key_span=None):
+        """key_span = (lo, hi): the key range this rank owns after the exchange (a hint for the local sort)."""
         from . import capi
 
         pc = capi.multi_push_constants(n, 32)
         if val0 is not None:
             self.handle.multi_sort_pairs(buf0, buf1, val0, val1, None, pc)
         else:
+            if key_span is not None:
+                self.handle.set_key_span_hint(*key_span)
             self.handle.multi_sort(buf0, buf1, None, pc)
+            if key_span is not None:
+                self.handle.set_key_span_hint()
 
     def empty(self, n):
         return self.torch.empty(max(1, n), dtype=self.torch.int32, device=self.device)
@@ -298,8 +303,15 @@ class DistributedSorter:
 
         # 5. local sort of this rank's key range
         if total_recv > 0:
+            # the keys this rank received: buckets [b_lo, b_hi) of bucket(key) = min(255, (key - key_base) >> shift)
+            b_lo, b_hi = int(plan.boundaries[self.rank]), int(plan.boundaries[self.rank + 1])
+            span_lo = min(0xFFFFFFFF, key_base + (b_lo << shift))
+            span_hi = 0xFFFFFFFF if b_hi >= NUM_BUCKETS else min(0xFFFFFFFF, key_base + (b_hi << shift) - 1)
+            if b_lo == 0:
+                span_lo = 0  # keys below key_base cannot occur, but the hint need not rely on it
             self.ops.local_sort(recv, self.recv[1][:total_recv], total_recv,
-                                recv_v, self.recv_vals[1][:total_recv] if recv_v is not None else None)
+                                recv_v, self.recv_vals[1][:total_recv] if recv_v is not None else None,
+                                key_span=(span_lo, max(span_lo, span_hi)))
         return (recv, recv_v) if values is not None else recv
 
 
