@@ -186,6 +186,52 @@ def test_key_span_hint(handle, dev, oracle):
     assert np.array_equal(out, np.sort(keys))
 
 
+def test_typed_keys_through_the_bucket_schedule(handle, dev, oracle):
+    """int32 / float32 keys on the bucket schedule: pass 1 reads the keys through the
+    order-preserving map, the local sort -- or the last fallback pass, or the plain map-back when no low bits
+    are left -- writes them back through the inverse.  Exact against numpy on the same bits."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(5)
+
+    def sort_typed(arr, key_type, schedule):
+        b0 = torch.from_numpy(arr.view(np.int32).copy()).to(dev)
+        b1 = torch.full_like(b0, 0x5A5A5A5A)
+        handle.set_schedule(schedule)
+        handle.multi_sort_typed(b0, b1, None, capi.multi_push_constants(arr.shape[0], 32), key_type)
+        handle.check_device_error()
+        return b0.cpu().numpy()
+
+    def float_order(f):
+        bits = f.view(np.uint32)
+        ordered = np.where(bits >> 31, ~bits, bits | np.uint32(0x80000000))
+        return f[np.argsort(ordered, kind="stable")]
+
+    for n, schedule in ((1, capi.SCHEDULE_BUCKET), (6145, capi.SCHEDULE_BUCKET), (300_001, capi.SCHEDULE_BUCKET),
+                        (5_000_011, capi.SCHEDULE_AUTO)):
+        ints = rng.integers(-(1 << 31), 1 << 31, size=n, dtype=np.int64).astype(np.int32)
+        assert np.array_equal(sort_typed(ints, capi.KEY_I32, schedule), np.sort(ints)), (n, "int32 uniform")
+        assert handle.bucket_stats()["fallback"] == 0
+        small = rng.integers(-100, 101, size=n, dtype=np.int64).astype(np.int32)  # two huge buckets: fallback passes undo the map
+        assert np.array_equal(sort_typed(small, capi.KEY_I32, schedule), np.sort(small)), (n, "int32 in [-100, 100]")
+        if n > 20_000:
+            assert handle.bucket_stats()["fallback"] == 1
+        nonneg = rng.integers(0, 1 << 16, size=n, dtype=np.int64).astype(np.int32)  # 16 varying bits: no local sort, plain map-back
+        assert np.array_equal(sort_typed(nonneg, capi.KEY_I32, schedule), np.sort(nonneg)), (n, "int32 in [0, 65535]")
+        st = handle.bucket_stats()
+        assert st["shift2"] == 0 and st["fallback"] == 0, st
+        f = (rng.standard_normal(n) * 1e6).astype(np.float32)
+        f[:: 7] = 0.0
+        f[1:: 11] = -0.0
+        f[2:: 13] = np.inf
+        f[3:: 17] = -np.inf
+        got = sort_typed(f, capi.KEY_F32, schedule).view(np.float32)
+        assert np.array_equal(got.view(np.uint32), float_order(f).view(np.uint32)), (n, "float32")
+        u = oracle.generate_random(n, 31 + n, 0xFFFFFFFF)
+        assert np.array_equal(sort_typed(u, capi.KEY_U32, schedule).view(np.uint32), np.sort(u)), (n, "uint32")
+    handle.set_schedule(capi.SCHEDULE_AUTO)
+
+
 def test_bucket_workspace_reuse_and_unaligned(handle, dev, oracle):
     """Sizes going up and down on one handle (the pass-1 piece table is cached per N) and key buffers
     that start at a 4-byte, not 16-byte, aligned address (no TMA: the workers copy the tiles in)."""

@@ -436,7 +436,7 @@ int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments,
     if (configured_device != h->device) {
         int r = set_smem(h, kernel, sizeof(MsdScatterSmem));
         if (r) return r;
-        r = set_smem(h, msd_local_tile_kernel, sizeof(LocalTileSmem));
+        r = set_smem(h, msd_local_tile_kernel<0>, sizeof(LocalTileSmem));
         if (r) return r;
         VKRS_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kernel, MSD_GROUPS * MSD_WORKERS + 32, sizeof(MsdScatterSmem)));
         if (blocks_per_sm < 1) return fail(h, VKRS_ERR_INTERNAL, "bucket scatter kernel does not fit on an SM");
@@ -471,6 +471,7 @@ int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments,
 // One digit pass of the bucket machinery: histogram of every piece, then the unstable scatter.  with_or: the
 // histogram also gathers the OR of all keys; gate: the histogram only works if *gate != 0 (recount);
 // do_count / do_scatter select the halves.
+template <int XF = 0>
 int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t ctas,
              uint32_t num_count_ctas, const uint32_t *bucket_start, uint32_t *sub_start, uint32_t max_sub, bool with_or,
              const uint32_t *gate, bool do_count, bool do_scatter, cudaStream_t s) {
@@ -479,15 +480,24 @@ int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *i
     if (do_count) {
         LaunchScope scope(h, gate ? "msd_piece_histogram_kernel<recount>" : "msd_piece_histogram_kernel", s);
         if (with_or)
-            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<true>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
+            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<true, XF>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
                                     w.plan, pass, w.hist[pass], gate));
         else
-            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
+            VKRS_CUDA(h, launch_pdl(msd_piece_histogram_kernel<false, XF>, dim3(num_count_ctas), dim3(MSD_HIST_THREADS), 0, s, in, pieces, num_pieces,
                                     w.plan, pass, w.hist[pass], gate));
     }
     if (do_scatter) {
         LaunchScope scope(h, "msd_scatter_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>, dim3(ctas), dim3(MSD_GROUPS * MSD_WORKERS + 32),
+        auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true, XF>;
+        if (XF != 0) {
+            static thread_local int configured_device = -1;
+            if (configured_device != h->device) {
+                int r = set_smem(h, kernel, sizeof(MsdScatterSmem));
+                if (r) return r;
+                configured_device = h->device;
+            }
+        }
+        VKRS_CUDA(h, launch_pdl(kernel, dim3(ctas), dim3(MSD_GROUPS * MSD_WORKERS + 32),
                                 sizeof(MsdScatterSmem), s, in, out, n, w.plan, pass, pieces, (const uint32_t *) w.seg_first[pass],
                                 (const uint32_t *) w.bucket_first[pass], bucket_start, (const uint32_t *) w.hist[pass], sub_start, max_sub));
     }
@@ -532,8 +542,11 @@ int lsd_unstable_first_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1,
     return VKRS_OK;
 }
 
-// The bucket schedule (see vkrs_msd.cuh).  Result in buf0.
-int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cudaStream_t s) {
+// The bucket schedule (see vkrs_msd.cuh).  Result in buf0.  XF != 0 (typed keys, KeyXform): pass 1 reads the keys
+// through the order-preserving map, everything in between works on mapped keys, the local sort (or the last
+// fallback pass) writes them back through the inverse map -- no extra pass, no extra traffic.
+template <int XF>
+int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cudaStream_t s) {
     uint32_t ctas, segments, seg_keys;
     int r = msd_prepare(h, n, ctas, segments, seg_keys);
     if (r) return r;
@@ -541,16 +554,16 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
     r = msd_begin(h, w, n, segments, seg_keys, h->msd_first_shift, h->msd_first_shift - 8, s);
     if (r) return r;
     // ---- pass 1: top digit, whole array = one bucket ----
-    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
+    r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
     if (r) return r;
     {
         LaunchScope scope(h, "msd_window_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_window_kernel, dim3(1), dim3(32), 0, s, w.plan));
     }
     // the recount only works when the keys have leading zero bits (the digit window moved)
-    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, false, &w.plan->recount, true, false, s);
+    r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, false, &w.plan->recount, true, false, s);
     if (r) return r;
-    r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, w.bucket_start, 0, false, nullptr, false, true, s);
+    r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, w.bucket_start, 0, false, nullptr, false, true, s);
     if (r) return r;
     if (h->msd_stop_after == 1) return VKRS_OK;
     // ---- pass 2: second digit inside each of the 256 buckets ----
@@ -577,8 +590,16 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
         }
         uint32_t grid = (uint32_t) (h->sm_count * 2);
         if (grid > item_stride - 1) grid = item_stride - 1;
+        if (XF != 0) {
+            static thread_local int configured_device = -1;
+            if (configured_device != h->device) {
+                r = set_smem(h, msd_local_tile_kernel<XF>, sizeof(LocalTileSmem));
+                if (r) return r;
+                configured_device = h->device;
+            }
+        }
         LaunchScope scope(h, "msd_local_tile_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
+        VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
                                 (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
                                 (const MsdPlan *) w.plan, h->msd_local_paths));
     }
@@ -586,12 +607,24 @@ int msd_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cu
     // ---- fallback: four stable LSD passes that only work if some bucket was too large ----
     for (int p = 0; p < 4; ++p) {
         uint32_t *in = (p & 1) ? buf1 : buf0, *out = (p & 1) ? buf0 : buf1;
-        r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s, 0, nullptr, true, true, nullptr,
-                                                         &w.plan->fallback);
+        if (p < 3 || XF == 0)
+            r = launch_seg_t<uint32_t, false, 384, 16, 2, 1>(h, in, out, nullptr, nullptr, n, 8 * p, s, 0, nullptr, true, true, nullptr,
+                                                             &w.plan->fallback);
+        else // typed keys: the last pass undoes the map
+            r = launch_seg_t<uint32_t, false, 384, 16, 2, 1, false, false, 0, XF>(h, in, out, nullptr, nullptr, n, 8 * p, s, 0, nullptr, true, true,
+                                                                                  nullptr, &w.plan->fallback);
         if (r) return r;
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;
+}
+
+// The schedule a keys-only whole sort of n keys runs (vkrs_schedule).
+int resolve_schedule(const vkrs_context *h, uint32_t n) {
+    if (h->schedule != VKRS_SCHEDULE_AUTO) return h->schedule;
+    if (h->variant != DEFAULT_VARIANT) return VKRS_SCHEDULE_LSD; // a tuning variant was picked: run exactly that kernel
+    if (n >= AUTO_BUCKET_MIN && n <= AUTO_BUCKET_MAX) return VKRS_SCHEDULE_BUCKET;
+    return n >= AUTO_UNSTABLE_FIRST_MIN ? VKRS_SCHEDULE_LSD_UNSTABLE_FIRST : VKRS_SCHEDULE_LSD;
 }
 
 int check_multi_pc(vkrs_context *h, const vkrs_multi_push_constants *pc, bool need_tiling) {
@@ -988,13 +1021,8 @@ int vkrs_multi_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, uint32_t *his
     if (!buf0 || !buf1) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int sched = h->schedule;
-    if (sched == VKRS_SCHEDULE_AUTO) {
-        if (h->variant != DEFAULT_VARIANT) sched = VKRS_SCHEDULE_LSD; // a tuning variant was picked: run exactly that kernel
-        else if (n >= AUTO_BUCKET_MIN && n <= AUTO_BUCKET_MAX) sched = VKRS_SCHEDULE_BUCKET;
-        else sched = n >= AUTO_UNSTABLE_FIRST_MIN ? VKRS_SCHEDULE_LSD_UNSTABLE_FIRST : VKRS_SCHEDULE_LSD;
-    }
-    if (sched == VKRS_SCHEDULE_BUCKET) return msd_sort_u32(h, buf0, buf1, n, s);
+    const int sched = resolve_schedule(h, n);
+    if (sched == VKRS_SCHEDULE_BUCKET) return msd_sort_t<0>(h, buf0, buf1, n, s);
     if (sched == VKRS_SCHEDULE_LSD_UNSTABLE_FIRST) return lsd_unstable_first_sort_u32(h, buf0, buf1, n, s);
     if (!variant_is_segmented(h->variant)) { // the single-sweep variants need the global digit starts
         const uint32_t tile = variant_tile(h->variant);
@@ -1022,10 +1050,11 @@ int vkrs_multi_sort_typed(vkrs_handle h, void *buf0, void *buf1, uint32_t *histo
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     uint32_t *b0 = static_cast<uint32_t *>(buf0), *b1 = static_cast<uint32_t *>(buf1);
+    const bool bucket = resolve_schedule(h, n) == VKRS_SCHEDULE_BUCKET; // else: four stable LSD passes
     switch (key_type) {
-        case VKRS_KEY_U32: return typed_sort_u32<0>(h, b0, b1, n, s);
-        case VKRS_KEY_I32: return typed_sort_u32<1>(h, b0, b1, n, s);
-        case VKRS_KEY_F32: return typed_sort_u32<2>(h, b0, b1, n, s);
+        case VKRS_KEY_U32: return bucket ? msd_sort_t<0>(h, b0, b1, n, s) : typed_sort_u32<0>(h, b0, b1, n, s);
+        case VKRS_KEY_I32: return bucket ? msd_sort_t<1>(h, b0, b1, n, s) : typed_sort_u32<1>(h, b0, b1, n, s);
+        case VKRS_KEY_F32: return bucket ? msd_sort_t<2>(h, b0, b1, n, s) : typed_sort_u32<2>(h, b0, b1, n, s);
         default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown key type %d", key_type);
     }
 }

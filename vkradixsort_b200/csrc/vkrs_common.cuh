@@ -169,6 +169,25 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t digit) {
     }
 }
 
+// Order-preserving key transforms fused into the first / last pass (the reference leaves signed and
+// floating-point keys to caller-side preprocessing, README.md:98-99,154-155).  fwd maps the key type's
+// order onto unsigned order, inv undoes it.  XF: 0 = unsigned (identity), 1 = two's-complement signed,
+// 2 = IEEE-754 binary32/binary64 (negative values reversed, -0 < +0, NaNs at the two ends by sign).
+template <typename KeyT, int XF>
+struct KeyXform {
+    static constexpr KeyT SIGN = KeyT(1) << (8 * sizeof(KeyT) - 1);
+    static __device__ __forceinline__ KeyT fwd(KeyT k) {
+        if (XF == 1) return k ^ SIGN;
+        if (XF == 2) return k ^ ((k & SIGN) ? ~KeyT(0) : SIGN);
+        return k;
+    }
+    static __device__ __forceinline__ KeyT inv(KeyT k) {
+        if (XF == 1) return k ^ SIGN;
+        if (XF == 2) return k ^ ((k & SIGN) ? SIGN : ~KeyT(0));
+        return k;
+    }
+};
+
 __device__ __forceinline__ uint32_t warp_inclusive_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

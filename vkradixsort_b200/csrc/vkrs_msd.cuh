@@ -197,7 +197,7 @@ msd_plan_pieces_kernel(const uint32_t *__restrict__ bucket_start, uint32_t B, ui
 // counter columns (bank == lane).  WITH_OR: also folds the OR of all keys into the plan.
 // gate (may be NULL): the kernel only works if *gate != 0.
 // =====================================================================================
-template <bool WITH_OR>
+template <bool WITH_OR, int XF = 0>
 __global__ void __launch_bounds__(MSD_HIST_THREADS)
 msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__restrict__ pieces,
                            const uint32_t *__restrict__ num_pieces, MsdPlan *plan, int pass, uint32_t *__restrict__ hist,
@@ -214,7 +214,8 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
     __syncthreads();
     uint32_t *my_col = cnt + lane;
     uint32_t acc_or = 0, acc_and = 0xFFFFFFFFu;
-    auto count_key = [&](uint32_t k) {
+    auto count_key = [&](uint32_t raw) {
+        const uint32_t k = KeyXform<uint32_t, XF>::fwd(raw); // typed keys: pass 1 reads them through the order-preserving map
         atomicAdd(my_col + msd_digit(k, shift) * 32, 1u);
         if (WITH_OR) {
             acc_or |= k;
@@ -299,7 +300,7 @@ struct MsdSmem {
     Group g[GROUPS];
 };
 
-template <int WORKERS, int KPT, int GROUPS, bool UNIFORM_FAST>
+template <int WORKERS, int KPT, int GROUPS, bool UNIFORM_FAST, int XF = 0>
 __global__ void __launch_bounds__(GROUPS * WORKERS + 32, 1)
 msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ keys_out, uint32_t n, MsdPlan *plan, int pass,
                    const uint4 *__restrict__ pieces, const uint32_t *__restrict__ seg_first,
@@ -432,7 +433,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             if (full) {
 #pragma unroll
                 for (int i = 0; i < KPT; ++i) {
-                    const uint32_t d = msd_digit(tin[chunk0 + i * 32], shift);
+                    const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), shift);
                     if (UNIFORM_FAST) {
                         const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
                         if (__all_sync(0xffffffffu, d == d_first)) {
@@ -451,7 +452,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                 for (int i = 0; i < KPT; ++i) {
                     const uint32_t idx = chunk0 + i * 32;
                     rk[i] = 0;
-                    if (idx - vlo < vcount) rk[i] = atomicAdd(&cnt[msd_digit(tin[idx], shift)], 1u);
+                    if (idx - vlo < vcount) rk[i] = atomicAdd(&cnt[msd_digit(KeyXform<uint32_t, XF>::fwd(tin[idx]), shift)], 1u);
                 }
             }
             named_bar_sync(bar_w, WORKERS); // (A) counts of tile jj final; sorted[] holds tile jj-1 completely
@@ -504,7 +505,8 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                     if (sub_start && q == qf) { // the bucket's first piece publishes the run starts
                         sub_start[b * RADIX + dgt] = run_start;
                         // pass 1: a top-digit bucket above 256 * LOCAL_MAX keys holds a 16-bit-prefix bucket above LOCAL_MAX
-                        if (pass == 0 && btotal > (uint32_t) (RADIX * LOCAL_MAX) && plan->shift[1] > 0) {
+                        // (not for typed keys: their fallback passes expect the transformed keys pass 2 leaves in buf0)
+                        if (XF == 0 && pass == 0 && btotal > (uint32_t) (RADIX * LOCAL_MAX) && plan->shift[1] > 0) {
                             plan->skip_pass2 = 1;
                             plan->fallback = 1;
                         }
@@ -526,7 +528,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             if (full) {
 #pragma unroll
                 for (int i = 0; i < KPT; ++i) {
-                    const uint32_t key = tin[chunk0 + i * 32];
+                    const uint32_t key = KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]);
                     s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
                 }
             } else {
@@ -534,7 +536,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                 for (int i = 0; i < KPT; ++i) {
                     const uint32_t idx = chunk0 + i * 32;
                     if (idx - vlo < vcount) {
-                        const uint32_t key = tin[idx];
+                        const uint32_t key = KeyXform<uint32_t, XF>::fwd(tin[idx]);
                         s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
                     }
                 }
@@ -697,7 +699,7 @@ __device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__r
 // Robust shared-memory sort of one bucket gk[0, cnt_keys), cnt_keys <= LOCAL_MAX, by its low 16 bits
 // (8 if !two_bytes).  All THREADS threads of the CTA call it.  a / b: LOCAL_MAX keys each; warp_cnt:
 // [THREADS/32][256]; small_cnt: 256; scratch: 8.
-template <int THREADS>
+template <int THREADS, int XF>
 __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uint32_t cnt_keys, bool two_bytes, uint32_t *a,
                                                   uint32_t *b, uint32_t *warp_cnt, uint32_t *small_cnt, uint32_t *scratch) {
     constexpr int WARPS = THREADS / 32;
@@ -754,7 +756,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
         for (int i = 0; i < KPT; ++i) {
             if (i < (int) rounds) {
                 const uint32_t p = tid + i * THREADS;
-                if (p < cnt_keys) gk[p] = b[p];
+                if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(b[p]);
             }
         }
         __syncthreads();
@@ -811,7 +813,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
     for (int i = 0; i < KPT; ++i) {
         if (i < (int) rounds) {
             const uint32_t p = tid + i * THREADS;
-            if (p < cnt_keys) gk[p] = a[p];
+            if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(a[p]);
         }
     }
     __syncthreads(); // a[] / b[] / counters are free again
@@ -819,6 +821,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
 
 // Bins path of one item: keys in `in[0, size)`, (key - base) >> s < LT_BINS; `grouped` is scratch.  Writes the
 // sorted item to gk[0, size) and returns false, or returns true (nothing written) when some bin is over-full.
+template <int XF>
 __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_t *in, uint32_t *grouped, uint32_t *__restrict__ gk,
                                                 uint32_t size, uint32_t base, uint32_t s) {
     const int tid = threadIdx.x;
@@ -883,7 +886,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     __syncthreads();
     if (s == 0) {
 #pragma unroll 4
-        for (uint32_t p = tid; p < size; p += LT_THREADS) gk[p] = grouped[p];
+        for (uint32_t p = tid; p < size; p += LT_THREADS) gk[p] = KeyXform<uint32_t, XF>::inv(grouped[p]);
         return false;
     }
 
@@ -904,11 +907,13 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
                 r += (o < k || (o == k && j < d)) ? 1u : 0u;
             }
         }
-        gk[lo + r] = k;
+        gk[lo + r] = KeyXform<uint32_t, XF>::inv(k);
     }
     return false;
 }
 
+// XF != 0 (typed keys): the keys in the array are the transformed ones; every key is written back through the inverse map.
+template <int XF>
 __global__ void __launch_bounds__(LT_THREADS, VKRS_LT_MIN_BLOCKS)
 msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start,
                       const uint32_t *__restrict__ item_first, const uint32_t *__restrict__ item_lo, uint32_t n,
@@ -919,7 +924,11 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     grid_dependency_wait();
     if (plan->fallback != 0) return;
     const uint32_t low_bits = plan->shift[1];
-    if (low_bits == 0) return;
+    if (low_bits == 0) { // nothing left to sort; typed keys still have to be mapped back
+        if (XF != 0)
+            for (uint32_t i = blockIdx.x * LT_THREADS + tid; i < n; i += gridDim.x * LT_THREADS) keys[i] = KeyXform<uint32_t, XF>::inv(keys[i]);
+        return;
+    }
     const bool two_bytes = low_bits > 8;
     // the bits above the two partition digits are shared by all keys (msd_window_kernel)
     const uint32_t common_high = low_bits + 16u >= 32u ? 0u : (plan->key_and & ~((1u << (low_bits + 16u)) - 1u));
@@ -959,7 +968,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                 uint32_t *gk = keys + lo;
                 if (paths & 2u) {
                     const uint32_t s = span_bits > (uint32_t) LT_BIN_BITS ? span_bits - (uint32_t) LT_BIN_BITS : 0u;
-                    todo = local_tile_bins(sm, in, sm.buf[b_sorted], gk, size, base, s);
+                    todo = local_tile_bins<XF>(sm, in, sm.buf[b_sorted], gk, size, base, s);
                 }
             }
             if (todo) {
@@ -974,17 +983,20 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                     }
                     sm.cand_lo[tid] = blo;
                     sm.cand_hi[tid] = bhi;
-                    if (__syncthreads_or(bhi - blo > 1) == 0) continue;
+                    if (__syncthreads_or(bhi - blo > (XF != 0 ? 0u : 1u)) == 0) continue;
                     const uint32_t chunk = j1 - jb < (uint32_t) LT_THREADS ? j1 - jb : (uint32_t) LT_THREADS;
                     for (uint32_t c = 0; c < chunk; ++c) {
                         const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
+                        if (XF != 0 && chi - clo == 1 && tid == 0) keys[clo] = KeyXform<uint32_t, XF>::inv(keys[clo]);
                         if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
-                            local_bucket_sort<LT_THREADS>(keys + clo, chi - clo, two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
+                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
                                                           sm.small_cnt, sm.scratch);
                     }
                     __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
                 }
             }
+        } else if (XF != 0 && size == 1 && tid == 0) {
+            keys[lo] = KeyXform<uint32_t, XF>::inv(keys[lo]);
         }
         lo = nlo;
         hi = nhi;

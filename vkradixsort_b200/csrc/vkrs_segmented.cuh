@@ -52,25 +52,6 @@ struct DigitOf {
     __device__ __forceinline__ DigitBitMasks bit_masks() const { return DigitBitMasks(PARTITION ? 0u : (shift & 31u)); }
 };
 
-// Order-preserving key transforms fused into the first / last pass (the reference leaves signed and
-// floating-point keys to caller-side preprocessing, README.md:98-99,154-155).  fwd maps the key type's
-// order onto unsigned order, inv undoes it.  XF: 0 = unsigned (identity), 1 = two's-complement signed,
-// 2 = IEEE-754 binary32/binary64 (negative values reversed, -0 < +0, NaNs at the two ends by sign).
-template <typename KeyT, int XF>
-struct KeyXform {
-    static constexpr KeyT SIGN = KeyT(1) << (8 * sizeof(KeyT) - 1);
-    static __device__ __forceinline__ KeyT fwd(KeyT k) {
-        if (XF == 1) return k ^ SIGN;
-        if (XF == 2) return k ^ ((k & SIGN) ? ~KeyT(0) : SIGN);
-        return k;
-    }
-    static __device__ __forceinline__ KeyT inv(KeyT k) {
-        if (XF == 1) return k ^ SIGN;
-        if (XF == 2) return k ^ ((k & SIGN) ? SIGN : ~KeyT(0));
-        return k;
-    }
-};
-
 // Tiles [first, first + count) of segment g when `num_tiles` tiles are dealt to `num_segments`
 // segments as evenly as possible (host and device agree through this one function).
 __host__ __device__ __forceinline__ void segment_tiles(uint32_t g, uint32_t num_segments, uint32_t num_tiles,
