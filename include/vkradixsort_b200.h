@@ -202,14 +202,16 @@ int vkrs_get_variant(vkrs_handle handle);
  *                        MultiRadixSort::execute loop (MultiRadixSort.cpp:56-61).
  *   LSD_UNSTABLE_FIRST   the same, but pass 0 ranks keys with one shared-memory atomic instead of the
  *                        stable ballot match: a first pass has no earlier order to preserve.
- *   BUCKET               two unstable passes on the two most significant digits (below the leading bits all
- *                        keys share), then every 16-bit-prefix bucket is sorted in shared memory.
+ *   BUCKET               two unstable passes on the two most significant digits of (key - smallest key), i.e. of
+ *                        the occupied key range, then every 16-bit-prefix bucket is sorted in shared memory.
  *                        Falls back to LSD on the device, without a host round trip, when a bucket is
  *                        larger than 4096 keys (heavily skewed input).  DESIGN.md 4.1.
  *   AUTO                 by N, from the measured crossovers: BUCKET for 4*10^6 .. 2.2*10^8 keys, LSD below,
  *                        LSD_UNSTABLE_FIRST above (LSD whenever a tuning variant other than the default was
  *                        selected with vkrs_set_variant).
- * Key+payload, 64-bit and typed sorts always run stable LSD passes. */
+ * int32 keys (vkrs_multi_sort_typed) follow the same rule; float32 keys stay on the LSD passes unless BUCKET is
+ * set explicitly (bell-shaped floats crowd into few 16-bit prefixes); key+payload and 64-bit sorts always run
+ * stable LSD passes. */
 typedef enum vkrs_schedule {
     VKRS_SCHEDULE_AUTO = 0,
     VKRS_SCHEDULE_LSD = 1,
@@ -221,13 +223,12 @@ int vkrs_set_schedule(vkrs_handle handle, int schedule);
 int vkrs_get_schedule(vkrs_handle handle);
 const char *vkrs_schedule_name(int schedule);
 /* Hint for the BUCKET schedule: all keys of the following keys-only sorts lie in [lo_key, hi_key] (e.g. one
- * rank's key range after the multi-GPU exchange).  The schedule finds the bits all keys share by itself and
- * skips them; with the hint its first histogram is already counted at the right digit position, which saves
- * one 4 B/key recount.  A wrong hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint. */
+ * rank's key range after the multi-GPU exchange).  The schedule finds the occupied key range by itself; with
+ * the hint its first histogram is already counted in the right digit window, which saves one 4 B/key recount.  A wrong hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint. */
 int vkrs_set_key_span_hint(vkrs_handle handle, uint32_t lo_key, uint32_t hi_key);
 /* Control words of the handle's last BUCKET sort, for tests and diagnostics: out8 = {shift of pass 1,
- * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, OR of all
- * keys, largest bucket seen if > 2048, pieces of pass 1, pieces of pass 2}.  Synchronises `stream`. */
+ * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, smallest key,
+ * largest bucket pass 2 saw, pieces of pass 1, pieces of pass 2}.  Synchronises `stream`. */
 int vkrs_bucket_stats(vkrs_handle handle, uint32_t *out8, void *stream);
 /* Test aid: end the BUCKET schedule after stage 1 (partition pass 1: keys grouped by the top digit, in
  * buf1), 2 (pass 2: grouped by the top two digits, in buf0) or 3 (local sort, fallback passes not

@@ -70,6 +70,8 @@ def distributions(oracle, n, seed):
         "hot_prefix": np.where(rng.random(n) < 0.5, np.uint32(0xABCD0000), 0).astype(np.uint32)
         | rng.integers(0, 1 << 16, n, dtype=np.uint32),  # half of the keys in one 16-bit-prefix bucket
         "low16_only_high_random": (rng.integers(0, 1 << 16, n, dtype=np.uint32) << 16).astype(np.uint32),
+        "around_2^31": (np.uint32(0x7FFFF000) + rng.integers(0, 0x2000, n, dtype=np.uint32)).astype(np.uint32),  # narrow range across a bit boundary
+        "offset_range": (np.uint32(123456789) + rng.integers(0, 3_000_000, n, dtype=np.uint32)).astype(np.uint32),
     }
 
 
@@ -108,11 +110,12 @@ def test_bucket_stages(handle, dev, oracle):
         st = handle.bucket_stats()
         assert st["shift1"] == s1 and st["shift2"] == s1 - 8, (name, st)
         assert st["recount"] == (1 if s1 != 24 else 0), (name, st)
-        d1 = (b1 >> np.uint32(s1)) & np.uint32(255)
+        base = np.uint32(st["key_min"] if st["recount"] else 0)  # the digits are taken from key - base (vkrs_msd.cuh)
+        d1 = ((b1 - base) >> np.uint32(s1)) & np.uint32(255)
         assert np.all(np.diff(d1.astype(np.int64)) >= 0), f"{name}: pass 1 output is not grouped by the top digit"
         assert np.array_equal(np.sort(b1), np.sort(keys)), f"{name}: pass 1 output is not a permutation of the input"
         b0, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=2)
-        d12 = (b0 >> np.uint32(s1 - 8)).astype(np.int64)
+        d12 = ((b0 - base) >> np.uint32(s1 - 8)).astype(np.int64)
         assert np.all(np.diff(d12) >= 0), f"{name}: pass 2 output is not grouped by the top two digits"
         assert np.array_equal(np.sort(b0), np.sort(keys)), f"{name}: pass 2 output is not a permutation of the input"
         b0, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=3)
@@ -141,7 +144,7 @@ def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
     st = handle.bucket_stats()
     assert st["fallback"] == 1 and st["max_bucket"] == 0 and st["shift1"] == 24, st
     assert np.array_equal(out0, np.sort(keys0))
-    # a prefix shared by ALL keys is no sort work: the digit window moves below it, two passes finish the job
+    # only the occupied key range is sort work: the digit window sits on (key - smallest key), two passes finish the job
     keys1 = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
     out1, _ = run_sort(handle, keys1, dev, capi.SCHEDULE_BUCKET)
     st = handle.bucket_stats()
@@ -212,8 +215,12 @@ def test_typed_keys_through_the_bucket_schedule(handle, dev, oracle):
         ints = rng.integers(-(1 << 31), 1 << 31, size=n, dtype=np.int64).astype(np.int32)
         assert np.array_equal(sort_typed(ints, capi.KEY_I32, schedule), np.sort(ints)), (n, "int32 uniform")
         assert handle.bucket_stats()["fallback"] == 0
-        small = rng.integers(-100, 101, size=n, dtype=np.int64).astype(np.int32)  # two huge buckets: fallback passes undo the map
+        small = rng.integers(-100, 101, size=n, dtype=np.int64).astype(np.int32)  # 201 values around zero: two passes, no local sort
         assert np.array_equal(sort_typed(small, capi.KEY_I32, schedule), np.sort(small)), (n, "int32 in [-100, 100]")
+        st = handle.bucket_stats()
+        assert st["fallback"] == 0 and st["shift2"] == 0, st
+        hot = np.where(rng.random(n) < 0.5, np.int32(5), ints).astype(np.int32)  # half of the keys equal: the fallback passes undo the map
+        assert np.array_equal(sort_typed(hot, capi.KEY_I32, schedule), np.sort(hot)), (n, "int32, one hot value")
         if n > 20_000:
             assert handle.bucket_stats()["fallback"] == 1
         nonneg = rng.integers(0, 1 << 16, size=n, dtype=np.int64).astype(np.int32)  # 16 varying bits: no local sort, plain map-back

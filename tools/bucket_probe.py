@@ -73,12 +73,13 @@ def diagnose(h, keys, want):
         torch.cuda.synchronize()
         st = h.bucket_stats()
         res = b1 if stage == 1 else b0
+        base = st["key_min"] if st["recount"] else 0  # the digits are taken from key - base
         perm_ok = bool(torch.equal(expect_sorted(res), want))
         if stage == 1:
-            d = (res >> st["shift1"]) & 255
+            d = ((res - base) >> st["shift1"]) & 255
             grouped = bool((d[1:] >= d[:-1]).all())
         elif stage == 2:
-            d = ((res >> st["shift2"]) & 0xFFFF).to(torch.int64)
+            d = (((res - base) >> st["shift2"]) & 0xFFFF).to(torch.int64)
             grouped = bool((d[1:] >= d[:-1]).all())
         else:
             grouped = first_bad(res, want) is None

@@ -322,7 +322,7 @@ class Handle:
         """Control words of the last bucket-schedule sort (synchronises the stream)."""
         out = (ctypes.c_uint32 * 8)()
         self._check(self._lib.vkrs_bucket_stats(self._h, out, _stream(stream)))
-        names = ("shift1", "shift2", "fallback", "recount", "key_or", "max_bucket", "pieces1", "pieces2")
+        names = ("shift1", "shift2", "fallback", "recount", "key_min", "max_bucket", "pieces1", "pieces2")
         return dict(zip(names, (int(v) for v in out)))
 
     def set_key_span_hint(self, lo_key: int = 0, hi_key: int = 0xFFFFFFFF):

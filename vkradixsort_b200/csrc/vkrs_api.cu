@@ -102,7 +102,7 @@ struct vkrs_context {
     uint32_t msd_segments_cap = 0; // segments the workspace was laid out for
     uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
     int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
-    uint32_t msd_first_shift = 24; // where the first histogram of the bucket schedule counts (vkrs_set_key_span_hint)
+    uint32_t msd_first_shift = 24, msd_first_base = 0; // digit window the first histogram of the bucket schedule counts in (vkrs_set_key_span_hint)
     uint32_t msd_local_paths = 3; // local sort: bit 0 bitmap path, bit 1 bins path (VKRS_LOCAL_PATHS, tuning / tests)
     uint32_t *msd_items = nullptr; // item_first[items + 1] | item_lo[items + 1] of the local sort
     uint64_t msd_items_cap = 0;
@@ -469,7 +469,7 @@ int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments,
 }
 
 // One digit pass of the bucket machinery: histogram of every piece, then the unstable scatter.  with_or: the
-// histogram also gathers the OR of all keys; gate: the histogram only works if *gate != 0 (recount);
+// histogram also gathers the smallest and the largest key; gate: the histogram only works if *gate != 0 (recount);
 // do_count / do_scatter select the halves.
 template <int XF = 0>
 int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *in, uint32_t *out, uint32_t n, uint32_t ctas,
@@ -506,10 +506,10 @@ int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *i
 
 // init + (cached per N) the piece table of the first pass: pieces == segments, one bucket [0, n)
 int msd_begin(vkrs_context *h, const MsdWorkspace &w, uint32_t n, uint32_t segments, uint32_t seg_keys, uint32_t shift0,
-              uint32_t shift1, cudaStream_t s) {
+              uint32_t shift1, uint32_t base0, cudaStream_t s) {
     {
         LaunchScope scope(h, "msd_init_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_init_kernel, dim3(1), dim3(32), 0, s, w.plan, shift0, shift1));
+        VKRS_CUDA(h, launch_pdl(msd_init_kernel, dim3(1), dim3(32), 0, s, w.plan, shift0, shift1, base0));
     }
     if (h->msd_plan_n != n || h->msd_plan_segments != segments || h->msd_plan_seg_keys != seg_keys) {
         LaunchScope scope(h, "msd_plan_pieces_kernel", s);
@@ -530,7 +530,7 @@ int lsd_unstable_first_sort_u32(vkrs_context *h, uint32_t *buf0, uint32_t *buf1,
     int r = msd_prepare(h, n, ctas, segments, seg_keys);
     if (r) return r;
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
-    r = msd_begin(h, w, n, segments, seg_keys, 0, 0, s);
+    r = msd_begin(h, w, n, segments, seg_keys, 0, 0, 0, s);
     if (r) return r;
     r = msd_pass(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, false, nullptr, true, true, s);
     if (r) return r;
@@ -551,7 +551,8 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
     int r = msd_prepare(h, n, ctas, segments, seg_keys);
     if (r) return r;
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
-    r = msd_begin(h, w, n, segments, seg_keys, h->msd_first_shift, h->msd_first_shift - 8, s);
+    const uint32_t shift0 = XF == 0 ? h->msd_first_shift : 24u; // the key-span hint is about raw keys
+    r = msd_begin(h, w, n, segments, seg_keys, shift0, shift0 - 8, XF == 0 ? h->msd_first_base : 0u, s);
     if (r) return r;
     // ---- pass 1: top digit, whole array = one bucket ----
     r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
@@ -903,12 +904,12 @@ const char *vkrs_schedule_name(int schedule) {
     }
 }
 
-// Control words of the last bucket-schedule sort: {shift1, shift2, fallback, recount, key_or, max_sub,
+// Control words of the last bucket-schedule sort: {shift1, shift2, fallback, recount, smallest key, max_sub,
 // pieces of pass 1, pieces of pass 2}.  Synchronises `stream`.
 int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (!out8) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "out8 is NULL");
-    static_assert(sizeof(MsdPlan) == 10 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
+    static_assert(sizeof(MsdPlan) == 11 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
     memset(out8, 0, 8 * sizeof(uint32_t));
     if (!h->msd_ws) return VKRS_OK;
     DeviceGuard guard(h->device);
@@ -919,8 +920,9 @@ int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
 }
 
 // Hint: the keys of the following keys-only sorts lie in [lo_key, hi_key].  The bucket schedule then counts its
-// first histogram directly below the bits lo_key and hi_key share; a wrong hint only costs the recount the
-// schedule does anyway when the digit window moves.  (0, 0xFFFFFFFF) = no hint.
+// first histogram in the digit window of that range (digits of key - lo_key, directly under the top bit of
+// hi_key - lo_key); a wrong hint only costs the recount the schedule does anyway when the window moves.
+// (0, 0xFFFFFFFF) = no hint.
 int vkrs_set_key_span_hint(vkrs_handle h, uint32_t lo_key, uint32_t hi_key) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (lo_key > hi_key) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "lo_key > hi_key");
@@ -928,6 +930,7 @@ int vkrs_set_key_span_hint(vkrs_handle h, uint32_t lo_key, uint32_t hi_key) {
     uint32_t top = 0;
     while (top < 31 && (x >> (top + 1)) != 0) ++top;
     h->msd_first_shift = top >= 15 ? top - 7 : 8;
+    h->msd_first_base = lo_key;
     return VKRS_OK;
 }
 
@@ -1054,7 +1057,9 @@ int vkrs_multi_sort_typed(vkrs_handle h, void *buf0, void *buf1, uint32_t *histo
     switch (key_type) {
         case VKRS_KEY_U32: return bucket ? msd_sort_t<0>(h, b0, b1, n, s) : typed_sort_u32<0>(h, b0, b1, n, s);
         case VKRS_KEY_I32: return bucket ? msd_sort_t<1>(h, b0, b1, n, s) : typed_sort_u32<1>(h, b0, b1, n, s);
-        case VKRS_KEY_F32: return bucket ? msd_sort_t<2>(h, b0, b1, n, s) : typed_sort_u32<2>(h, b0, b1, n, s);
+        // float32: sign + exponent + 7 mantissa bits make the 16-bit prefix, which bell-shaped data crowds into a few
+        // hundred buckets -- the fallback would be the rule; auto keeps them on the LSD passes, BUCKET can be forced
+        case VKRS_KEY_F32: return h->schedule == VKRS_SCHEDULE_BUCKET ? msd_sort_t<2>(h, b0, b1, n, s) : typed_sort_u32<2>(h, b0, b1, n, s);
         default: return fail(h, VKRS_ERR_INVALID_ARGUMENT, "unknown key type %d", key_type);
     }
 }

@@ -11,11 +11,12 @@
 // sort is unique, so the output is bit-identical to the reference's (testSort:
 // multiradixsort/src/MultiRadixSort.cpp:148-161).  Key+payload sorts keep the stable LSD passes.
 //
-// Schedule for N keys (8-bit digits as in multi_radixsort.comp:12,100; `top` = highest set bit of
-// the OR of all keys, so leading zero bits -- the reference's 28-bit test keys,
-// MultiRadixSort.cpp:126 -- cost nothing):
-//   pass 1   digit (key >> s1) & 255, s1 = top-7 : piece histogram + unstable scatter  buf0 -> buf1
-//   pass 2   digit (key >> s2) & 255, s2 = s1-8, inside each of the 256 buckets of pass 1
+// Schedule for N keys (8-bit digits as in multi_radixsort.comp:12,100; the digits are taken from
+// key - kmin, `top` = highest set bit of kmax - kmin, so only the OCCUPIED key range is sort work:
+// leading zero bits -- the reference's 28-bit test keys, MultiRadixSort.cpp:126 --, a shared prefix,
+// small signed integers around zero all cost nothing):
+//   pass 1   digit ((key - kmin) >> s1) & 255, s1 = top-7 : piece histogram + unstable scatter  buf0 -> buf1
+//   pass 2   digit ((key - kmin) >> s2) & 255, s2 = s1-8, inside each of the 256 buckets of pass 1
 //                                                : piece histogram + unstable scatter  buf1 -> buf0
 //   local    every (digit1, digit2) bucket (N / 65536 keys on average) is sorted by its remaining low
 //            bits inside shared memory, in place in buf0 : one unstable + one stable 8-bit pass.
@@ -41,12 +42,13 @@ namespace vkrs {
 struct MsdPlan {
     uint32_t shift[2];      // digit shift of partition pass 1 / 2; shift[1] is also the number of low bits left to the local sort
     uint32_t fallback;      // != 0: some bucket is too large for the local sort -> the stable LSD passes run
-    uint32_t recount;       // != 0: the pass-1 histogram was counted at the wrong shift and is counted again
-    uint32_t key_or;        // OR of all keys (only gathered by the first histogram)
-    uint32_t max_sub;       // diagnostic: size of the largest (digit1, digit2) bucket seen
+    uint32_t recount;       // != 0: the pass-1 histogram was counted in the wrong digit window and is counted again
+    uint32_t key_min;       // smallest key (gathered by the first histogram, with key_max)
+    uint32_t max_sub;       // size of the largest (digit1, digit2) bucket pass 2 saw
     uint32_t num_pieces[2]; // pieces of pass 1 / 2 (NOT reset per sort: the pass-1 plan is cached per N)
-    uint32_t key_and;       // AND of all keys (gathered with key_or): bits on which all keys agree are no sort work
+    uint32_t key_max;       // largest key
     uint32_t skip_pass2;    // != 0: pass 1 already saw a bucket that is bound to overflow the local sort; pass 2 is not run
+    uint32_t base;          // the digits are taken from key - base: the occupied key range starts at digit value 0
 };
 
 constexpr int MSD_PLAN_THREADS = 1024;
@@ -55,7 +57,8 @@ constexpr int LOCAL_THREADS = 256;
 constexpr int LOCAL_KPT = 16;
 constexpr int LOCAL_MAX = LOCAL_THREADS * LOCAL_KPT; // largest bucket the local sort takes
 
-__device__ __forceinline__ uint32_t msd_digit(uint32_t key, uint32_t shift) { return (key >> shift) & (RADIX - 1); }
+// digit of a key: 8 bits of its distance from the base of the occupied key range
+__device__ __forceinline__ uint32_t msd_digit(uint32_t key, uint32_t base, uint32_t shift) { return ((key - base) >> shift) & (RADIX - 1); }
 
 // Exclusive scan of one value per thread over a 1024-thread block.  scratch = 33 uint32.
 __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t *scratch, uint32_t *total_out) {
@@ -76,35 +79,44 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32
     return r;
 }
 
-// Start of a sort: default digit positions, flags down.
-__global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1) {
+// Start of a sort: where the first histogram counts (base 0, top byte unless a key-span hint says otherwise), flags down.
+__global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1, uint32_t base0) {
     grid_dependency_wait();
     if (threadIdx.x == 0) {
         plan->shift[0] = shift0;
         plan->shift[1] = shift1;
+        plan->base = base0;
         plan->fallback = 0;
         plan->recount = 0;
-        plan->key_or = 0;
-        plan->key_and = 0xFFFFFFFFu;
+        plan->key_min = 0xFFFFFFFFu;
+        plan->key_max = 0;
         plan->max_sub = 0;
         plan->skip_pass2 = 0;
     }
 }
 
-// After the first histogram: put the two partition digits directly under the highest bit on which the
-// keys differ (leading bits shared by all keys -- zeros of small keys, the common prefix of one rank's
-// key range after the multi-GPU exchange -- are no sort work).
+// After the first histogram: the digits are taken from (key - smallest key), the two partition digits directly
+// under the highest set bit of (largest - smallest key).  So only the OCCUPIED key range is sort work: leading zero
+// bits (the reference's 28-bit test keys, MultiRadixSort.cpp:126), the shared prefix of one rank's key range after
+// the multi-GPU exchange, small signed integers around zero (after the sign-flip map) all spread over the 65536
+// buckets.  The histogram is only counted again when it was not already counted in that window.
 __global__ void msd_window_kernel(MsdPlan *plan) {
     grid_dependency_wait();
     if (threadIdx.x == 0) {
-        const uint32_t varying = plan->key_or & ~plan->key_and;
-        // all keys equal: nothing to sort; one bucket, no low bits left, no fallback
-        const uint32_t top = varying != 0 ? 31u - (uint32_t) __clz((int) varying) : 0u;
-        const uint32_t s1 = top >= 15u ? top - 7u : 8u;
-        if (s1 != plan->shift[0]) {
-            plan->shift[0] = s1;
-            plan->shift[1] = s1 - 8u;
-            plan->recount = 1;
+        const uint32_t kmin = plan->key_min, kmax = plan->key_max;
+        if (kmin <= kmax) {
+            const uint32_t span = kmax - kmin;
+            // all keys equal: nothing to sort; one bucket, no low bits left, no fallback
+            const uint32_t top = span != 0 ? 31u - (uint32_t) __clz((int) span) : 0u;
+            const uint32_t s1 = top >= 15u ? top - 7u : 8u;
+            const uint32_t base0 = plan->base;
+            const bool keep = base0 <= kmin && plan->shift[0] == s1 && ((kmax - base0) >> s1) < (uint32_t) RADIX;
+            if (!keep) {
+                plan->base = kmin;
+                plan->shift[0] = s1;
+                plan->shift[1] = s1 - 8u;
+                plan->recount = 1;
+            }
         }
     }
 }
@@ -194,7 +206,7 @@ msd_plan_pieces_kernel(const uint32_t *__restrict__ bucket_start, uint32_t B, ui
 // =====================================================================================
 // hist[q][d] = #{keys of piece q whose digit is d}  (multi_radixsort_histograms.comp:31-56 with the
 // work group's slab replaced by the piece).  One CTA per piece; 128-bit streaming loads; lane-private
-// counter columns (bank == lane).  WITH_OR: also folds the OR of all keys into the plan.
+// counter columns (bank == lane).  WITH_OR: also folds the smallest and the largest key into the plan.
 // gate (may be NULL): the kernel only works if *gate != 0.
 // =====================================================================================
 template <bool WITH_OR, int XF = 0>
@@ -210,16 +222,16 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
     if (pass == 1 && plan->skip_pass2 != 0) return;
     if (blockIdx.x >= *num_pieces) return;
     const uint4 pc = pieces[blockIdx.x];
-    const uint32_t shift = plan->shift[pass];
+    const uint32_t shift = plan->shift[pass], kbase = plan->base;
     __syncthreads();
     uint32_t *my_col = cnt + lane;
-    uint32_t acc_or = 0, acc_and = 0xFFFFFFFFu;
+    uint32_t acc_min = 0xFFFFFFFFu, acc_max = 0;
     auto count_key = [&](uint32_t raw) {
         const uint32_t k = KeyXform<uint32_t, XF>::fwd(raw); // typed keys: pass 1 reads them through the order-preserving map
-        atomicAdd(my_col + msd_digit(k, shift) * 32, 1u);
+        atomicAdd(my_col + msd_digit(k, kbase, shift) * 32, 1u);
         if (WITH_OR) {
-            acc_or |= k;
-            acc_and &= k;
+            acc_min = min(acc_min, k);
+            acc_max = max(acc_max, k);
         }
     };
     {
@@ -256,11 +268,11 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
         hist[(size_t) blockIdx.x * RADIX + tid] = total;
     }
     if (WITH_OR) {
-        acc_or = __reduce_or_sync(0xffffffffu, acc_or);
-        acc_and = __reduce_and_sync(0xffffffffu, acc_and);
-        if (lane == 0) {
-            if (acc_or != 0) atomicOr(&plan->key_or, acc_or);
-            if (acc_and != 0xFFFFFFFFu) atomicAnd(&plan->key_and, acc_and);
+        acc_min = __reduce_min_sync(0xffffffffu, acc_min);
+        acc_max = __reduce_max_sync(0xffffffffu, acc_max);
+        if (lane == 0 && acc_min <= acc_max) {
+            atomicMin(&plan->key_min, acc_min);
+            atomicMax(&plan->key_max, acc_max);
         }
     }
 }
@@ -388,7 +400,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
     Group &s = sm.g[grp];
     const uint32_t seg = blockIdx.x * GROUPS + grp;
     const uint32_t bar_w = 1 + grp, bar_d = 1 + GROUPS + grp; // this group's worker / digit named barriers
-    const uint32_t shift = plan->shift[pass];
+    const uint32_t shift = plan->shift[pass], kbase = plan->base;
     const uint32_t chunk0 = warp * (KPT * 32) + lane; // warp-striped: lane l reads chunk[i*32 + l]
     const bool is_digit_thread = gtid < RADIX;
     const uint32_t dgt = gtid, dwarp = dgt >> 5;
@@ -402,7 +414,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             const uint32_t p = gtid + k * WORKERS;
             if (p < count) {
                 const uint32_t key = s.sorted[p];
-                keys_out[s.bin_dst[pslot][msd_digit(key, shift)] + p] = key;
+                keys_out[s.bin_dst[pslot][msd_digit(key, kbase, shift)] + p] = key;
             }
         }
     };
@@ -433,7 +445,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             if (full) {
 #pragma unroll
                 for (int i = 0; i < KPT; ++i) {
-                    const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), shift);
+                    const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift);
                     if (UNIFORM_FAST) {
                         const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
                         if (__all_sync(0xffffffffu, d == d_first)) {
@@ -452,7 +464,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                 for (int i = 0; i < KPT; ++i) {
                     const uint32_t idx = chunk0 + i * 32;
                     rk[i] = 0;
-                    if (idx - vlo < vcount) rk[i] = atomicAdd(&cnt[msd_digit(KeyXform<uint32_t, XF>::fwd(tin[idx]), shift)], 1u);
+                    if (idx - vlo < vcount) rk[i] = atomicAdd(&cnt[msd_digit(KeyXform<uint32_t, XF>::fwd(tin[idx]), kbase, shift)], 1u);
                 }
             }
             named_bar_sync(bar_w, WORKERS); // (A) counts of tile jj final; sorted[] holds tile jj-1 completely
@@ -529,7 +541,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 #pragma unroll
                 for (int i = 0; i < KPT; ++i) {
                     const uint32_t key = KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]);
-                    s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
+                    s.sorted[cnt[msd_digit(key, kbase, shift)] + rk[i]] = key;
                 }
             } else {
 #pragma unroll
@@ -537,7 +549,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                     const uint32_t idx = chunk0 + i * 32;
                     if (idx - vlo < vcount) {
                         const uint32_t key = KeyXform<uint32_t, XF>::fwd(tin[idx]);
-                        s.sorted[cnt[msd_digit(key, shift)] + rk[i]] = key;
+                        s.sorted[cnt[msd_digit(key, kbase, shift)] + rk[i]] = key;
                     }
                 }
             }
@@ -696,11 +708,11 @@ __device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__r
     cp_async_commit();
 }
 
-// Robust shared-memory sort of one bucket gk[0, cnt_keys), cnt_keys <= LOCAL_MAX, by its low 16 bits
-// (8 if !two_bytes).  All THREADS threads of the CTA call it.  a / b: LOCAL_MAX keys each; warp_cnt:
+// Robust shared-memory sort of one bucket gk[0, cnt_keys), cnt_keys <= LOCAL_MAX, whose keys all lie in
+// [bias, bias + 2^16): by the low 16 bits of key - bias (8 if !two_bytes).  All THREADS threads of the CTA call it.  a / b: LOCAL_MAX keys each; warp_cnt:
 // [THREADS/32][256]; small_cnt: 256; scratch: 8.
 template <int THREADS, int XF>
-__device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uint32_t cnt_keys, bool two_bytes, uint32_t *a,
+__device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uint32_t cnt_keys, uint32_t bias, bool two_bytes, uint32_t *a,
                                                   uint32_t *b, uint32_t *warp_cnt, uint32_t *small_cnt, uint32_t *scratch) {
     constexpr int WARPS = THREADS / 32;
     constexpr int KPT = LOCAL_MAX / THREADS;
@@ -723,7 +735,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
     for (int i = 0; i < KPT; ++i) {
         if (i < (int) rounds) {
             const uint32_t p = tid + i * THREADS;
-            key[i] = p < cnt_keys ? ld_stream(gk + p) : 0xFFFFFFFFu;
+            key[i] = p < cnt_keys ? ld_stream(gk + p) - bias : 0xFFFFFFFFu; // distance from the bucket's first key value: < 2^16
         }
     }
     __syncthreads();
@@ -756,7 +768,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
         for (int i = 0; i < KPT; ++i) {
             if (i < (int) rounds) {
                 const uint32_t p = tid + i * THREADS;
-                if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(b[p]);
+                if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(b[p] + bias);
             }
         }
         __syncthreads();
@@ -813,7 +825,7 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
     for (int i = 0; i < KPT; ++i) {
         if (i < (int) rounds) {
             const uint32_t p = tid + i * THREADS;
-            if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(a[p]);
+            if (p < cnt_keys) gk[p] = KeyXform<uint32_t, XF>::inv(a[p] + bias);
         }
     }
     __syncthreads(); // a[] / b[] / counters are free again
@@ -930,8 +942,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         return;
     }
     const bool two_bytes = low_bits > 8;
-    // the bits above the two partition digits are shared by all keys (msd_window_kernel)
-    const uint32_t common_high = low_bits + 16u >= 32u ? 0u : (plan->key_and & ~((1u << (low_bits + 16u)) - 1u));
+    const uint32_t kbase = plan->base; // bucket j holds the keys kbase + (j << low_bits) + [0, 2^low_bits)
     const uint32_t window = lt_window(plan->max_sub);
     const uint32_t num_items = (n + window - 1) / window;
 
@@ -960,10 +971,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         if (size > 1) {
             bool todo = true;
             if (size <= (uint32_t) LT_CAP) {
-                // the item's buckets are j0 .. j1-1 and a key of bucket j is common_high + (j << low_bits) + its low bits
+                // the item's buckets are j0 .. j1-1 and a key of bucket j is kbase + (j << low_bits) + its low bits
                 const uint32_t nb = j1 - j0; // >= 1
                 const uint32_t span_bits = low_bits + (nb > 1 ? 32u - (uint32_t) __clz((int) (nb - 1)) : 0u);
-                const uint32_t base = common_high | (j0 << low_bits);
+                const uint32_t base = kbase + (j0 << low_bits);
                 const uint32_t *in = sm.buf[b_in] + (lo & 3u);
                 uint32_t *gk = keys + lo;
                 if (paths & 2u) {
@@ -989,7 +1000,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                         const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
                         if (XF != 0 && chi - clo == 1 && tid == 0) keys[clo] = KeyXform<uint32_t, XF>::inv(keys[clo]);
                         if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
-                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
+                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, kbase + ((jb + c) << low_bits), two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
                                                           sm.small_cnt, sm.scratch);
                     }
                     __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
