@@ -677,6 +677,7 @@ struct LocalTileSmem {
     uint32_t small_cnt[RADIX];                         // bucket path: byte-0 counters
     uint32_t cand_lo[LT_THREADS], cand_hi[LT_THREADS]; // bucket path: bounds of one chunk of buckets
     uint32_t scratch[40];
+    uint32_t params[4]; // loop invariants that are only needed once per item: kept out of the registers
 };
 
 __device__ __forceinline__ void cp_async_4(uint32_t *smem_dst, const uint32_t *gmem_src) {
@@ -941,8 +942,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
             for (uint32_t i = blockIdx.x * LT_THREADS + tid; i < n; i += gridDim.x * LT_THREADS) keys[i] = KeyXform<uint32_t, XF>::inv(keys[i]);
         return;
     }
-    const bool two_bytes = low_bits > 8;
-    const uint32_t kbase = plan->base; // bucket j holds the keys kbase + (j << low_bits) + [0, 2^low_bits)
+    if (tid == 0) {
+        sm.params[0] = plan->base; // bucket j holds the keys base + (j << low_bits) + [0, 2^low_bits)
+        sm.params[1] = paths;
+    }
     const uint32_t window = lt_window(plan->max_sub);
     const uint32_t num_items = (n + window - 1) / window;
 
@@ -974,10 +977,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                 // the item's buckets are j0 .. j1-1 and a key of bucket j is kbase + (j << low_bits) + its low bits
                 const uint32_t nb = j1 - j0; // >= 1
                 const uint32_t span_bits = low_bits + (nb > 1 ? 32u - (uint32_t) __clz((int) (nb - 1)) : 0u);
-                const uint32_t base = kbase + (j0 << low_bits);
+                const uint32_t base = sm.params[0] + (j0 << low_bits);
                 const uint32_t *in = sm.buf[b_in] + (lo & 3u);
                 uint32_t *gk = keys + lo;
-                if (paths & 2u) {
+                if (sm.params[1] & 2u) {
                     const uint32_t s = span_bits > (uint32_t) LT_BIN_BITS ? span_bits - (uint32_t) LT_BIN_BITS : 0u;
                     todo = local_tile_bins<XF>(sm, in, sm.buf[b_sorted], gk, size, base, s);
                 }
@@ -1000,7 +1003,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                         const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
                         if (XF != 0 && chi - clo == 1 && tid == 0) keys[clo] = KeyXform<uint32_t, XF>::inv(keys[clo]);
                         if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
-                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, kbase + ((jb + c) << low_bits), two_bytes, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
+                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, sm.params[0] + ((jb + c) << low_bits), low_bits > 8, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
                                                           sm.small_cnt, sm.scratch);
                     }
                     __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
