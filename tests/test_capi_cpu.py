@@ -54,6 +54,19 @@ def test_version_and_variants(built_lib):
     assert all(capi.variant_name(v) for v in range(capi.num_variants()))
 
 
+def test_schedule_names(built_lib):
+    """vkrs_schedule: the four keys-only schedules are named and numbered as include/vkradixsort_b200.h says."""
+    from vkradixsort_b200 import capi
+
+    assert (capi.SCHEDULE_AUTO, capi.SCHEDULE_LSD, capi.SCHEDULE_LSD_UNSTABLE_FIRST, capi.SCHEDULE_BUCKET) == (0, 1, 2, 3)
+    names = [capi.schedule_name(i) for i in range(capi.NUM_SCHEDULES)]
+    assert names[0] == "auto" and "lsd" in names[1] and "unstable" in names[2] and "bucket" in names[3]
+    assert capi.schedule_name(capi.NUM_SCHEDULES) == ""
+    header = open(os.path.join(ROOT, "include", "vkradixsort_b200.h")).read()
+    for i, sym in enumerate(("VKRS_SCHEDULE_AUTO", "VKRS_SCHEDULE_LSD", "VKRS_SCHEDULE_LSD_UNSTABLE_FIRST", "VKRS_SCHEDULE_BUCKET")):
+        assert f"{sym} = {i}" in header
+
+
 def test_facade_sizing_without_gpu(built_lib):
     from vkradixsort_b200 import GPUContext, MultiRadixSortPass
 
