@@ -7,7 +7,8 @@
 // least-significant-digit sort needs from every pass but its first.  A most-significant-digit split
 // needs none: the order inside a bucket is irrelevant because the bucket is sorted completely
 // afterwards.  Without stability a key's place in its tile is ONE shared-memory atomic
-// (rank = atomicAdd(count[digit], 1)), ~3x fewer instructions per key.  The result of a keys-only
+// (rank = atomicAdd(count[digit], 1)): 48 instead of 74 instructions, 17 instead of 23 shared-memory
+// wavefronts per 32 keys (measured, profiles/README.md).  The result of a keys-only
 // sort is unique, so the output is bit-identical to the reference's (testSort:
 // multiradixsort/src/MultiRadixSort.cpp:148-161).  Key+payload sorts keep the stable LSD passes.
 //
@@ -18,8 +19,10 @@
 //   pass 1   digit ((key - kmin) >> s1) & 255, s1 = top-7 : piece histogram + unstable scatter  buf0 -> buf1
 //   pass 2   digit ((key - kmin) >> s2) & 255, s2 = s1-8, inside each of the 256 buckets of pass 1
 //                                                : piece histogram + unstable scatter  buf1 -> buf0
-//   local    every (digit1, digit2) bucket (N / 65536 keys on average) is sorted by its remaining low
-//            bits inside shared memory, in place in buf0 : one unstable + one stable 8-bit pass.
+//   local    the (digit1, digit2) buckets (N / 65536 keys on average), batched into items of whole buckets
+//            that fit a shared-memory buffer, are sorted in shared memory, in place in buf0: 4096
+//            order-preserving bins ranked with atomics + a comparison fix-up inside the bins
+//            (msd_local_tile_kernel below).
 // A "piece" is the part of one bucket that lies inside one segment (a contiguous slab of the array
 // owned by one worker group): the reference's "work group w owns nb*256 consecutive keys"
 // (multi_radixsort_histograms.comp:43) cut at bucket boundaries, because a most-significant-digit
@@ -29,9 +32,12 @@
 //
 // The schedule depends on the key distribution: a (digit1, digit2) bucket larger than LOCAL_MAX keys
 // cannot be finished in shared memory.  That is detected on the device while pass 2 runs (the bucket
-// sizes fall out of its prologue); the plan's `fallback` word is raised, the local sort does nothing
-// and the four stable LSD passes that are enqueued behind it -- and otherwise exit at once -- sort
-// buf0.  No host round trip, everything stays stream-ordered.
+// sizes fall out of its prologue) -- or already in pass 1, when a top-digit bucket exceeds
+// 256 * LOCAL_MAX keys and pass 2 is then not run at all; the plan's `fallback` word is raised, the
+// local sort does nothing and the four stable LSD passes that are enqueued behind it -- and otherwise
+// exit at once -- sort buf0.  No host round trip, everything stays stream-ordered.
+// Typed keys (XF != 0, KeyXform in vkrs_common.cuh): pass 1 reads the keys through the order-preserving
+// map, the local sort (or the last fallback pass) writes them back through its inverse.
 #pragma once
 #include "vkrs_async.cuh"
 #include "vkrs_common.cuh"
