@@ -1,0 +1,91 @@
+"""CPU tests of the bucket schedule's logic through its numpy model (oracle/bucket_model.py): the digit window on
+the occupied key range, the recount rule, the two fallback rules, the item windows and the bin map + fix-up of
+the local sort -- against std::sort order (MultiRadixSort::testSort, multiradixsort/src/MultiRadixSort.cpp:148-161).
+The same inputs and the same expected control words are asserted on the device in tests/test_gpu_bucket.py."""
+import numpy as np
+import pytest
+
+from oracle import bucket_model as M
+
+
+def distributions(oracle, n, seed):
+    ar = np.arange(n, dtype=np.uint64)
+    rng = np.random.default_rng(seed)
+    return {
+        "uniform32": oracle.generate_random(n, seed, 0xFFFFFFFF),
+        "reference28": oracle.generate_random(n, seed + 1, 0x0FFFFFFF),  # MultiRadixSort.cpp:126
+        "bits20": oracle.generate_random(n, seed + 2, 0x000FFFFF),
+        "bits12": oracle.generate_random(n, seed + 3, 0x00000FFF),
+        "sorted": (ar * 4294967295 // max(n, 1)).astype(np.uint32),
+        "all_equal": np.full(n, 0xDEADBEEF, dtype=np.uint32),
+        "two_valued": ((ar % 2) * 0xFFFFFFFF).astype(np.uint32),
+        "hot_prefix": (np.where(rng.random(n) < 0.5, np.uint32(0xABCD0000), 0).astype(np.uint32)
+                       | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32),
+        "around_2^31": (np.uint32(0x7FFFF000) + rng.integers(0, 0x2000, n, dtype=np.uint32)).astype(np.uint32),
+        "offset_range": (np.uint32(123456789) + rng.integers(0, 3_000_000, n, dtype=np.uint32)).astype(np.uint32),
+        "clustered_low_bits": ((rng.integers(0, 1 << 14, n, dtype=np.uint32) << 18) | rng.integers(0, 4, n, dtype=np.uint32)).astype(np.uint32),
+    }
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 6145, 70_001])
+def test_model_sorts_every_distribution(oracle, n):
+    for name, keys in distributions(oracle, n, 4242 + n).items():
+        out, plan = M.sort(keys, seed=n)
+        assert oracle.test_sort(np.sort(keys), out) == -1, (n, name, plan)
+        assert plan.shift2 == plan.shift1 - 8 and 8 <= plan.shift1 <= 24, (name, plan)
+        assert int(keys.min()) >= plan.base, (name, plan)
+        assert ((int(keys.max()) - plan.base) >> plan.shift1) < 256, (name, plan)
+
+
+def test_digit_window_and_recount(oracle):
+    n = 100_003
+    # full-range keys: counted at (0, 24) from the start, nothing to redo
+    _, p = M.sort(oracle.generate_random(n, 1, 0xFFFFFFFF))
+    assert (p.base, p.shift1, p.shift2, p.recount, p.fallback) == (0, 24, 16, False, False)
+    # the reference's 28-bit keys: the window moves under bit 27, the first histogram is counted again
+    keys = oracle.generate_random(n, 2, 0x0FFFFFFF)
+    _, p = M.sort(keys)
+    assert (p.shift1, p.shift2, p.recount, p.base) == (20, 12, True, int(keys.min()))
+    # one rank's key range after the multi-GPU exchange: shared top bits
+    keys = (np.uint32(0xC0000000) | (oracle.generate_random(n, 9, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32)
+    _, p = M.sort(keys)
+    assert (p.shift1, p.recount) == (22, True)
+    _, p = M.sort(keys, hint=(0xC0000000, 0xFFFFFFFF))   # the exchange tells the local sort its key range
+    assert (p.shift1, p.recount, p.base) == (22, False, 0xC0000000)
+    _, p = M.sort(keys, hint=(0, 0xFFFF))                # a wrong hint only costs the recount
+    assert (p.shift1, p.recount) == (22, True)
+    # 16 varying bits: two passes are the whole sort, no local sort, never a fallback
+    keys = (np.uint32(0x12340000) | np.random.default_rng(7).integers(0, 1 << 16, 300_000, dtype=np.uint32)).astype(np.uint32)
+    out, p = M.sort(keys)
+    assert (p.shift1, p.shift2, p.fallback) == (8, 0, False) and np.array_equal(out, np.sort(keys))
+    # small signed integers around zero after the sign-flip map of vkrs_multi_sort_typed
+    ints = np.random.default_rng(8).integers(-100, 101, 50_000).astype(np.int32)
+    mapped = (ints.view(np.uint32) ^ np.uint32(0x80000000))
+    out, p = M.sort(mapped)
+    assert (p.shift2, p.fallback) == (0, False) and np.array_equal(out, np.sort(mapped))
+
+
+def test_fallback_rules(oracle):
+    rng = np.random.default_rng(7)
+    n = 300_000
+    # four 16-bit-prefix buckets of 75,000 keys: pass 2 sees the overflow
+    keys = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
+    out, p = M.sort(keys)
+    assert p.fallback and not p.skip_pass2 and p.max_bucket > M.LOCAL_MAX and p.shift1 == 24
+    assert np.array_equal(out, np.sort(keys))
+    # a top-digit bucket above 256 * 4096 keys: pass 1 already knows, pass 2 is skipped
+    m = 3_000_000
+    keys = ((rng.integers(0, 2, m, dtype=np.uint32) * np.uint32(0xFF000000)) | rng.integers(0, 1 << 24, m, dtype=np.uint32)).astype(np.uint32)
+    out, p = M.sort(keys)
+    assert p.fallback and p.skip_pass2 and p.max_bucket == 0 and p.shift1 == 24
+    assert np.array_equal(out, np.sort(keys))
+    # uniform keys never fall back below 2.2e8 keys: the largest of 65536 buckets stays far below 4096
+    _, p = M.sort(oracle.generate_random(2_000_003, 5, 0xFFFFFFFF))
+    assert not p.fallback and p.max_bucket < 100
+
+
+def test_item_windows():
+    assert M.lt_window(0) == 4096 and M.lt_window(1716) == 4096 and M.lt_window(2048) == 4096
+    assert M.lt_window(2049) == 2048 and M.lt_window(4096) == 2048 and M.lt_window(5000) == 1024
+    assert M.lt_window(6000) == 256  # cannot fit: such items go to the per-bucket path
+    assert M.hint_window(0, 0xFFFFFFFF) == (0, 24) and M.hint_window(0xC0000000, 0xFFFFFFFF) == (0xC0000000, 22)
