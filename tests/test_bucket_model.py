@@ -89,3 +89,23 @@ def test_item_windows():
     assert M.lt_window(2049) == 2048 and M.lt_window(4096) == 2048 and M.lt_window(5000) == 1024
     assert M.lt_window(6000) == 256  # cannot fit: such items go to the per-bucket path
     assert M.hint_window(0, 0xFFFFFFFF) == (0, 24) and M.hint_window(0xC0000000, 0xFFFFFFFF) == (0xC0000000, 22)
+
+
+def test_model_property_random_masks_and_offsets():
+    """Random sizes, bit masks, offsets and duplicate levels: the model's output is the sorted input and its
+    digit window always covers the occupied key range."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=120, deadline=None)
+    @given(n=st.integers(1, 3000), mask_bits=st.integers(0, 32), offset=st.integers(0, 0xFFFFFFFF), distinct=st.integers(1, 5000),
+           seed=st.integers(0, 2**31))
+    def check(n, mask_bits, offset, distinct, seed):
+        rng = np.random.default_rng(seed)
+        mask = (1 << mask_bits) - 1
+        pool = (rng.integers(0, 1 << 32, size=distinct, dtype=np.uint64) & np.uint64(mask))
+        keys = ((pool[rng.integers(0, distinct, size=n)] + np.uint64(offset)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        out, plan = M.sort(keys, seed=seed)
+        assert np.array_equal(out, np.sort(keys)), plan
+        assert plan.base <= int(keys.min()) and ((int(keys.max()) - plan.base) >> plan.shift1) < 256
+
+    check()
