@@ -387,7 +387,11 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
 #define VKRS_MSD_KPT 16
 #define VKRS_MSD_GROUPS 2
 #endif
+#ifndef VKRS_MSD_UNIFORM_FAST
+#define VKRS_MSD_UNIFORM_FAST 1
+#endif
 constexpr int MSD_WORKERS = VKRS_MSD_WORKERS, MSD_KPT = VKRS_MSD_KPT, MSD_GROUPS = VKRS_MSD_GROUPS;
+constexpr bool MSD_UNIFORM_FAST = VKRS_MSD_UNIFORM_FAST != 0;
 constexpr uint32_t MSD_TILE = MSD_WORKERS * MSD_KPT;
 constexpr uint32_t MSD_SUBS = RADIX * RADIX;          // (digit1, digit2) buckets
 // vkrs_multi_sort, schedule auto (measured crossovers, profiles/r01_schedule_sweep.jsonl): the bucket schedule wins
@@ -430,7 +434,7 @@ struct MsdWorkspace {
 using MsdScatterSmem = MsdSmem<MSD_WORKERS, MSD_KPT, MSD_GROUPS>;
 
 int msd_prepare(vkrs_context *h, uint32_t n, uint32_t &ctas, uint32_t &segments, uint32_t &seg_keys) {
-    auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true>;
+    auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, MSD_UNIFORM_FAST>;
     static thread_local int configured_device = -1;
     static thread_local int blocks_per_sm = 0;
     if (configured_device != h->device) {
@@ -488,7 +492,7 @@ int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *i
     }
     if (do_scatter) {
         LaunchScope scope(h, "msd_scatter_kernel", s);
-        auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, true, XF>;
+        auto kernel = msd_scatter_kernel<MSD_WORKERS, MSD_KPT, MSD_GROUPS, MSD_UNIFORM_FAST, XF>;
         if (XF != 0) {
             static thread_local int configured_device = -1;
             if (configured_device != h->device) {
@@ -589,7 +593,7 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
             VKRS_CUDA(h, launch_pdl(msd_items_kernel, dim3(MSD_SUBS / 256), dim3(256), 0, s, (const uint32_t *) w.sub_start, MSD_SUBS, n,
                                     item_first, item_lo, item_stride, (const MsdPlan *) w.plan));
         }
-        uint32_t grid = (uint32_t) (h->sm_count * 2);
+        uint32_t grid = (uint32_t) (h->sm_count * VKRS_LT_MIN_BLOCKS);
         if (grid > item_stride - 1) grid = item_stride - 1;
         if (XF != 0) {
             static thread_local int configured_device = -1;
@@ -602,7 +606,7 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
         LaunchScope scope(h, "msd_local_tile_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
                                 (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
-                                (const MsdPlan *) w.plan, h->msd_local_paths));
+                                (const MsdPlan *) w.plan, h->msd_local_paths, h->debug_counters));
     }
     if (h->msd_stop_after == 3) return VKRS_OK;
     // ---- fallback: four stable LSD passes that only work if some bucket was too large ----

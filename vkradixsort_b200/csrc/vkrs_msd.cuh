@@ -604,23 +604,28 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 #ifndef VKRS_LT_MIN_BLOCKS
 #define VKRS_LT_MIN_BLOCKS 2
 #endif
-constexpr int LT_THREADS = 512;
+#ifndef VKRS_LT_THREADS
+#define VKRS_LT_THREADS 512
+#endif
+constexpr int LT_THREADS = VKRS_LT_THREADS;
 constexpr int LT_CAP = VKRS_LT_CAP; // keys per shared-memory buffer: the largest item the bins path takes
 constexpr int LT_MIN_WINDOW = 256;
 constexpr int LT_BIN_BITS = VKRS_LT_BIN_BITS;
 constexpr int LT_BINS = 1 << LT_BIN_BITS;
-constexpr int LT_BIN_LIMIT = 32;
+constexpr int LT_BIN_LIMIT = 32; // power of two (the over-full test ORs the counts)
 constexpr int LT_BPT = LT_BINS / LT_THREADS; // bins per thread in the scan: LT_BPT / 4 conflict-free 128-bit accesses
 constexpr int LT_WORK_WORDS = LT_BINS > (LT_THREADS / 32) * RADIX ? LT_BINS : (LT_THREADS / 32) * RADIX;
 static_assert(LT_BPT % 4 == 0 && LT_BPT >= 4, "whole 128-bit groups of bins per thread");
-static_assert(LT_CAP >= LOCAL_MAX && LT_CAP < 8192, "part sums of the scan are packed two per word below; buffers double as the bucket path's a[] / b[]");
+static_assert(LT_CAP >= LOCAL_MAX && LT_CAP < 65536, "part sums of the scan are packed two per word below; buffers double as the bucket path's a[] / b[]");
 
-// Window of the item table for a largest bucket of max_sub keys: the largest power of two with
-// window + max_sub <= LT_CAP (an item then fits a buffer), at least LT_MIN_WINDOW.
+// Window of the item table for a largest bucket of max_sub keys: the largest multiple of 512 with
+// window + max_sub <= LT_CAP - 4 (an item then fits a buffer), at least LT_MIN_WINDOW.
 __host__ __device__ __forceinline__ uint32_t lt_window(uint32_t max_sub) {
-    uint32_t w = 4096;
-    while (w > (uint32_t) LT_MIN_WINDOW && w + max_sub > (uint32_t) LT_CAP) w >>= 1;
-    return w;
+    const uint32_t room = (uint32_t) LT_CAP - 4u; // the bins path takes items of up to LT_CAP - 4 keys
+    if (max_sub + (uint32_t) LT_MIN_WINDOW >= room) return (uint32_t) LT_MIN_WINDOW;
+    uint32_t w = (room - max_sub) & ~511u;
+    if (w < (uint32_t) LT_MIN_WINDOW) w = (uint32_t) LT_MIN_WINDOW;
+    return w > 16384u ? 16384u : w;
 }
 
 // TRAILING_SYNC = false: the caller guarantees a barrier before scratch is written again.
@@ -682,8 +687,10 @@ struct LocalTileSmem {
     alignas(16) uint32_t work_m[4 + LT_WORK_WORDS];
     uint32_t small_cnt[RADIX];                         // bucket path: byte-0 counters
     uint32_t cand_lo[LT_THREADS], cand_hi[LT_THREADS]; // bucket path: bounds of one chunk of buckets
-    uint32_t scratch[40];
-    uint32_t params[4]; // loop invariants that are only needed once per item: kept out of the registers
+    uint32_t scratch[72];
+    uint32_t params[8]; // loop invariants that are only needed once per item: kept out of the registers
+    unsigned long long timers[16]; // phase timers of thread 0 (tuning aid, vkrs_debug_counters)
+    unsigned long long t_last;
 };
 
 __device__ __forceinline__ void cp_async_4(uint32_t *smem_dst, const uint32_t *gmem_src) {
@@ -838,47 +845,132 @@ __device__ __forceinline__ void local_bucket_sort(uint32_t *__restrict__ gk, uin
     __syncthreads(); // a[] / b[] / counters are free again
 }
 
-// Bins path of one item: keys in `in[0, size)`, (key - base) >> s < LT_BINS; `grouped` is scratch.  Writes the
-// sorted item to gk[0, size) and returns false, or returns true (nothing written) when some bin is over-full.
-template <int XF>
-__device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_t *in, uint32_t *grouped, uint32_t *__restrict__ gk,
-                                                uint32_t size, uint32_t base, uint32_t s) {
+// Exclusive scan of TWO independent values per thread (v.x, v.y) over the block in one go.  scratch = 66 uint32.
+// TRAILING_SYNC = false: the caller guarantees a barrier before scratch is written again.
+template <int THREADS, bool TRAILING_SYNC = true>
+__device__ __forceinline__ uint2 block_exclusive_scan2_t(uint2 v, uint32_t *scratch /* 66 */, uint2 *total_out) {
+    static_assert(THREADS % 32 == 0 && THREADS <= 1024, "whole warps");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint2 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t tx = __shfl_up_sync(0xffffffffu, incl.x, o), ty = __shfl_up_sync(0xffffffffu, incl.y, o);
+        if (lane >= o) {
+            incl.x += tx;
+            incl.y += ty;
+        }
+    }
+    if (lane == 31) {
+        scratch[warp] = incl.x;
+        scratch[33 + warp] = incl.y;
+    }
+    __syncthreads();
+    if (warp < 2) { // warp 0 scans the x sums, warp 1 the y sums
+        uint32_t *sc = scratch + 33 * warp;
+        const uint32_t w = lane < THREADS / 32 ? sc[lane] : 0u;
+        const uint32_t wi = warp_inclusive_scan(w, lane);
+        sc[lane] = wi - w;
+        if (lane == 31) sc[32] = wi;
+    }
+    __syncthreads();
+    const uint2 r = make_uint2(scratch[warp] + incl.x - v.x, scratch[33 + warp] + incl.y - v.y);
+    if (total_out) *total_out = make_uint2(scratch[32], scratch[65]);
+    if (TRAILING_SYNC) __syncthreads();
+    return r;
+}
+
+// Bin map of an item that spans `span` key values: bin = umulhi(key - base, mult) with
+// mult = floor(LT_BINS * 2^32 / span) -- order preserving, uses ALL bins whatever the span (a shift would leave up to
+// half of them empty), always < LT_BINS.  lt_bin_mult() returns 0 when the span fits the bins ("exact mode": the caller
+// then passes mult = 2^32 - 1 and base one less, which makes bin = key - base; equal bins are equal keys and nothing
+// has to be fixed up).
+__device__ __forceinline__ uint32_t lt_bin_mult(uint32_t num_buckets, uint32_t low_bits) {
+    const uint64_t span = (uint64_t) num_buckets << low_bits;
+    if (span <= (uint64_t) LT_BINS) return 0u;
+    // floor(LT_BINS * 2^32 / span) to 21 bits, rounded DOWN (never above the exact quotient: the bin stays < LT_BINS;
+    // a few of the topmost bins may go unused) -- a single-precision division instead of a 64-bit one per item
+    const float q = __fdividef((float) LT_BINS * 4294967296.0f, (float) span) * (1.0f - 1.0f / 2097152.0f);
+    return (uint32_t) q;
+}
+
+// Phase timers (tuning aid): thread 0 adds the clocks since the last mark to slot `i`.  Compiled in with -DVKRS_LT_TIMERS.
+#ifdef VKRS_LT_TIMERS
+#define LT_MARK(sm, i)                                        \
+    do {                                                      \
+        if (threadIdx.x == 0) {                               \
+            const unsigned long long now__ = clock64();       \
+            (sm).timers[i] += now__ - (sm).t_last;            \
+            (sm).t_last = now__;                              \
+        }                                                     \
+    } while (0)
+#else
+#define LT_MARK(sm, i) do { } while (0)
+#endif
+// Where position p of a sorted item is kept in shared memory: the low two bits are flipped by bits 5-6, so that the
+// fix-up's stores (lane l owns positions 4l .. 4l+3: a stride of four words) and the copy-out's loads (lane l reads
+// position base + l) both touch 32 different banks.
+// Bins path of one item: keys in `in[0, size)`, size <= LT_CAP - 4, umulhi(key - base, mult) < LT_BINS for every key;
+// `gbuf` is a 16-byte aligned scratch buffer.  Leaves the key of final position p in obuf[off + p] (obuf + off may be,
+// and is, `in`) and returns false, or returns true (`in` untouched) when some bin is over-full.
+//   count   one shared-memory atomic per key
+//   scan    the bins' first positions
+//   place   a second atomic on the bin's running position: the keys, grouped by bin, in gbuf[4 .. 4 + size)
+//   fix-up  position p ranks its key among the keys of its bin by (key, offset inside the bin).  The first four
+//           keys from the bin's start are compared without a branch: a key read past the bin's end belongs to a
+//           later bin and is larger (the map is monotone), so it never counts.  Larger bins (rare: the expected
+//           bin holds about one key) finish in a loop.
+__device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_t *in, uint32_t *gbuf, uint32_t *obuf, uint32_t off,
+                                                uint32_t size, uint32_t base, uint32_t mult, bool exact) {
     const int tid = threadIdx.x;
     uint32_t *cnt = sm.work_m + 4;
     uint4 *cv = reinterpret_cast<uint4 *>(cnt);
+    uint32_t *grouped = gbuf + 4;
     constexpr int PARTS = LT_BPT / 4; // thread t owns bins [4t, 4t+4) of each of PARTS equal parts of the bin range
 #pragma unroll
     for (int k = 0; k < PARTS; ++k) cv[k * LT_THREADS + tid] = make_uint4(0, 0, 0, 0);
     if (tid == 0) sm.work_m[3] = 0;
     __syncthreads();
+    LT_MARK(sm, 2);
 
     // ---- count: one shared-memory reduction per key ----
 #pragma unroll 4
-    for (uint32_t p = tid; p < size; p += LT_THREADS) atomicAdd(&cnt[(in[p] - base) >> s], 1u);
+    for (uint32_t p = tid; p < size; p += LT_THREADS) atomicAdd(&cnt[__umulhi(in[p] - base, mult)], 1u);
+    LT_MARK(sm, 3);
     __syncthreads();
+    LT_MARK(sm, 4);
 
-    // ---- scan: conflict-free 128-bit accesses; the part sums (< 2^13) are scanned two per word ----
+    // ---- scan: conflict-free 128-bit accesses; the part sums (< 2^16) are scanned two per word ----
     {
-        static_assert(PARTS == 2 || PARTS == 4, "two or four parts");
-        uint32_t sum[PARTS], maxc = 0;
+        static_assert(PARTS == 2 || PARTS == 4 || PARTS == 8, "two, four or eight parts");
+        uint32_t sum[PARTS], orc = 0;
 #pragma unroll
         for (int k = 0; k < PARTS; ++k) {
             const uint4 v = cv[k * LT_THREADS + tid];
             sum[k] = v.x + v.y + v.z + v.w;
-            maxc = max(max(maxc, max(v.x, v.y)), max(v.z, v.w));
+            orc |= v.x | v.y | v.z | v.w;
         }
         uint32_t run[PARTS];
-        {
+        if (PARTS == 2) {
             uint32_t total = 0;
-            const uint32_t ex = block_exclusive_scan_t<LT_THREADS, PARTS == 4>(sum[0] | (sum[1] << 16), sm.scratch, &total); // a barrier follows below
+            const uint32_t ex = block_exclusive_scan_t<LT_THREADS, false>(sum[0] | (sum[1] << 16), sm.scratch, &total); // a barrier follows below
             run[0] = ex & 0xffffu;
             run[1] = (ex >> 16) + (total & 0xffffu);
-            if (PARTS == 4) {
-                const uint32_t first_half = (total & 0xffffu) + (total >> 16);
-                uint32_t total2 = 0;
-                const uint32_t ex2 = block_exclusive_scan_t<LT_THREADS, false>(sum[PARTS - 2] | (sum[PARTS - 1] << 16), sm.scratch, &total2);
-                run[PARTS - 2] = first_half + (ex2 & 0xffffu);
-                run[PARTS - 1] = first_half + (ex2 >> 16) + (total2 & 0xffffu);
+        } else {
+            uint32_t part_base = 0;
+#pragma unroll
+            for (int k = 0; k < PARTS; k += 4) {
+                uint2 total;
+                const uint2 ex = block_exclusive_scan2_t<LT_THREADS, false>(
+                    make_uint2(sum[k] | (sum[k + 1] << 16), sum[k + 2] | (sum[k + 3] << 16)), sm.scratch, &total);
+                if (k + 4 < PARTS) __syncthreads(); // scratch is reused by the next round
+                run[k] = part_base + (ex.x & 0xffffu);
+                part_base += total.x & 0xffffu;
+                run[k + 1] = part_base + (ex.x >> 16);
+                part_base += total.x >> 16;
+                run[k + 2] = part_base + (ex.y & 0xffffu);
+                part_base += total.y & 0xffffu;
+                run[k + 3] = part_base + (ex.y >> 16);
+                part_base += total.y >> 16;
             }
         }
 #pragma unroll
@@ -891,44 +983,80 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
             o.w = o.z + v.z;
             cv[k * LT_THREADS + tid] = o;
         }
-        // equal bins are equal keys when s == 0: nothing to fix up, any bin size is fine
-        if (__syncthreads_or(s > 0 && maxc > (uint32_t) LT_BIN_LIMIT)) return true;
+        // equal bins are equal keys in exact mode: nothing to fix up, any bin size is fine
+        if (__syncthreads_or(!exact && orc >= (uint32_t) LT_BIN_LIMIT)) return true;
     }
+    LT_MARK(sm, 5);
 
     // ---- place: a second atomic on the bin's running prefix hands out the positions; afterwards
-    //      cnt[bin] = one past the last position of the bin, cnt[bin - 1] = its first ----
+    //      cnt[bin] = one past the last position of the bin, cnt[bin - 1] = its first.  (`gbuf` may still hold the
+    //      previous item's output until the barrier behind the count: first touched here) ----
+    if (tid < 4) grouped[size + tid] = 0xFFFFFFFFu; // the fix-up reads up to three keys past its bin: never smaller than a key
 #pragma unroll 4
     for (uint32_t p = tid; p < size; p += LT_THREADS) {
         const uint32_t k = in[p];
-        grouped[atomicAdd(&cnt[(k - base) >> s], 1u)] = k;
+        grouped[atomicAdd(&cnt[__umulhi(k - base, mult)], 1u)] = k;
     }
+    LT_MARK(sm, 6);
     __syncthreads();
-    if (s == 0) {
+    LT_MARK(sm, 7);
+    if (exact) {
 #pragma unroll 4
-        for (uint32_t p = tid; p < size; p += LT_THREADS) gk[p] = KeyXform<uint32_t, XF>::inv(grouped[p]);
+        for (uint32_t p = tid; p < size; p += LT_THREADS) obuf[off + p] = grouped[p];
         return false;
     }
 
-    // ---- fix-up, straight to global memory: position p ranks its key among the keys of its bin by
-    //      (key, offset inside the bin); the key only moves inside its bin, so the stores stay nearly coalesced ----
+    // ---- fix-up, one position per thread: the bin's bounds from the counter array, the first four keys of the bin
+    //      compared without a branch (a key read past the bin's end belongs to a later bin and is larger), a loop
+    //      for larger bins ----
 #pragma unroll 2
     for (uint32_t p = tid; p < size; p += LT_THREADS) {
         const uint32_t k = grouped[p];
-        const uint32_t bin = (k - base) >> s;
+        const uint32_t bin = __umulhi(k - base, mult);
         const uint32_t lo = cnt[(int) bin - 1], n = cnt[bin] - lo, d = p - lo;
-        uint32_t r = d;
-        if (n > 1) {
-            const uint32_t *g = grouped + lo;
-            r = 0;
+        const uint32_t *g = grouped + lo;
+        const uint64_t me = ((uint64_t) k << 32) | d;
+        uint32_t r = lo;
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) r += ((((uint64_t) g[j] << 32) | j) < me) ? 1u : 0u;
+        if (n > 4) {
 #pragma unroll 1
-            for (uint32_t j = 0; j < n; ++j) { // one loop over the whole bin: two loops around the own slot diverge more (708 vs 585 us)
-                const uint32_t o = g[j];
-                r += (o < k || (o == k && j < d)) ? 1u : 0u;
+            for (uint32_t j = 4; j < n; ++j) r += ((((uint64_t) g[j] << 32) | j) < me) ? 1u : 0u;
+        }
+        obuf[off + r] = k;
+    }
+    LT_MARK(sm, 8);
+    return false;
+}
+
+// Copies a sorted item (local_tile_bins) from shared memory back to its place: buf[(lo & 3) + p] -> keys[lo + p],
+// 128-bit loads and stores where whole 16-byte groups of the array belong to the item.
+template <int XF>
+__device__ __forceinline__ void store_item(const uint32_t *buf, uint32_t *__restrict__ keys, uint32_t lo, uint32_t size, bool base_aligned) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t off = lo & 3u, a0 = lo - off, hi = lo + size;
+    if (base_aligned) {
+        const uint32_t groups = (off + size + 3u) >> 2;
+        for (uint32_t g = tid; g < groups; g += LT_THREADS) {
+            uint4 v = *reinterpret_cast<const uint4 *>(buf + 4u * g);
+            v.x = KeyXform<uint32_t, XF>::inv(v.x);
+            v.y = KeyXform<uint32_t, XF>::inv(v.y);
+            v.z = KeyXform<uint32_t, XF>::inv(v.z);
+            v.w = KeyXform<uint32_t, XF>::inv(v.w);
+            const uint32_t at = a0 + 4u * g;
+            if (at >= lo && at + 4u <= hi) {
+                *reinterpret_cast<uint4 *>(keys + at) = v;
+            } else { // the first / last group may be shared with the neighbouring items
+                if (at + 0u >= lo && at + 0u < hi) keys[at + 0u] = v.x;
+                if (at + 1u >= lo && at + 1u < hi) keys[at + 1u] = v.y;
+                if (at + 2u >= lo && at + 2u < hi) keys[at + 2u] = v.z;
+                if (at + 3u >= lo && at + 3u < hi) keys[at + 3u] = v.w;
             }
         }
-        gk[lo + r] = KeyXform<uint32_t, XF>::inv(k);
+    } else {
+#pragma unroll 4
+        for (uint32_t p = tid; p < size; p += LT_THREADS) keys[lo + p] = KeyXform<uint32_t, XF>::inv(buf[off + p]);
     }
-    return false;
 }
 
 // XF != 0 (typed keys): the keys in the array are the transformed ones; every key is written back through the inverse map.
@@ -936,7 +1064,8 @@ template <int XF>
 __global__ void __launch_bounds__(LT_THREADS, VKRS_LT_MIN_BLOCKS)
 msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start,
                       const uint32_t *__restrict__ item_first, const uint32_t *__restrict__ item_lo, uint32_t n,
-                      const MsdPlan *__restrict__ plan, uint32_t paths /* bit 1 clear: bucket path only (tests) */) {
+                      const MsdPlan *__restrict__ plan, uint32_t paths /* bit 1 clear: bucket path only (tests) */,
+                      unsigned long long *__restrict__ timers_out) {
     extern __shared__ __align__(128) unsigned char smem_raw_tile[];
     LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_tile);
     const int tid = threadIdx.x;
@@ -957,12 +1086,24 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
 
     uint32_t w = blockIdx.x;
     if (w >= num_items) return;
-    // descriptors one item ahead of the keys, keys one item ahead of the sort
+    // descriptors one item ahead of the keys, keys one item ahead of the sort.  (Measured alternatives, both slower:
+    // descriptors fetched further ahead into a shared-memory ring by a plain load left in flight -- every later
+    // instruction that shares its scoreboard slot waits for it, and the warp that issued it arrives late at each
+    // barrier, +75 us -- or by cp.async together with the keys, +50 us.)
     uint32_t lo = __ldcg(item_lo + w), hi = __ldcg(item_lo + w + 1);
     uint32_t j0 = __ldcg(item_first + w), j1 = __ldcg(item_first + w + 1);
     uint32_t b_in = 0, b_sorted = 1, b_next = 2; // roles of the three key buffers
     const bool base_aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
     prefetch_item(sm.buf[b_in], keys, lo, hi, n, base_aligned);
+    if (tid == 0) sm.params[2] = lt_bin_mult(j1 > j0 ? j1 - j0 : 1u, low_bits); // the bin map of an item is computed one item ahead
+#ifdef VKRS_LT_TIMERS
+    if (tid == 0) {
+        for (int i = 0; i < 16; ++i) sm.timers[i] = 0;
+        sm.t_last = clock64();
+    }
+#endif
+    uint32_t mslot = 0;
+    uint32_t pend_lo = 0, pend_size = 0; // the previous item, sorted, waits in buf[b_sorted] for its copy back to the array
     for (; w < num_items; w += gridDim.x) {
         const uint32_t wn = w + gridDim.x;
         uint32_t nlo = 0, nhi = 0, nj0 = 0, nj1 = 0;
@@ -974,21 +1115,30 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         }
         const uint32_t size = hi - lo;
         cp_async_wait_all();
-        __syncthreads(); // this item's keys are in buf[b_in]; buf[b_next] and the work area are free
+        LT_MARK(sm, 9);
+        __syncthreads(); // this item's keys are in buf[b_in]; buf[b_next] and the work area are free; buf[b_sorted] = previous item, sorted
+        LT_MARK(sm, 0);
         // ---- start the copy of the next item: it has the whole of this item's sort to land ----
         prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned);
+        if (tid == 0) sm.params[2 + (mslot ^ 1)] = lt_bin_mult(nj1 > nj0 ? nj1 - nj0 : 1u, low_bits);
+        // ---- the previous item goes back to the array while this one is counted (buf[b_sorted] is first written two barriers on) ----
+        if (pend_size != 0) store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+        pend_size = 0;
+        LT_MARK(sm, 1);
         if (size > 1) {
             bool todo = true;
             if (size <= (uint32_t) LT_CAP) {
                 // the item's buckets are j0 .. j1-1 and a key of bucket j is kbase + (j << low_bits) + its low bits
-                const uint32_t nb = j1 - j0; // >= 1
-                const uint32_t span_bits = low_bits + (nb > 1 ? 32u - (uint32_t) __clz((int) (nb - 1)) : 0u);
                 const uint32_t base = sm.params[0] + (j0 << low_bits);
-                const uint32_t *in = sm.buf[b_in] + (lo & 3u);
-                uint32_t *gk = keys + lo;
-                if (sm.params[1] & 2u) {
-                    const uint32_t s = span_bits > (uint32_t) LT_BIN_BITS ? span_bits - (uint32_t) LT_BIN_BITS : 0u;
-                    todo = local_tile_bins<XF>(sm, in, sm.buf[b_sorted], gk, size, base, s);
+                uint32_t *in = sm.buf[b_in] + (lo & 3u);
+                if ((sm.params[1] & 2u) && size <= (uint32_t) LT_CAP - 4u) {
+                    const uint32_t mult = sm.params[2 + mslot];
+                    const bool exact = mult == 0;
+                    todo = local_tile_bins(sm, in, sm.buf[b_sorted], sm.buf[b_in], lo & 3u, size, exact ? base - 1u : base, exact ? 0xFFFFFFFFu : mult, exact);
+                }
+                if (!todo) {
+                    pend_lo = lo;
+                    pend_size = size;
                 }
             }
             if (todo) {
@@ -1018,15 +1168,27 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         } else if (XF != 0 && size == 1 && tid == 0) {
             keys[lo] = KeyXform<uint32_t, XF>::inv(keys[lo]);
         }
+        LT_MARK(sm, 11);
         lo = nlo;
         hi = nhi;
         j0 = nj0;
         j1 = nj1;
-        const uint32_t t = b_in; // rotate: next keys <- prefetched, sorted scratch <- old keys, prefetch target <- old scratch
+        mslot ^= 1;
+        const uint32_t t = b_in; // rotate: next keys <- prefetched, sorted scratch <- old keys (= the sorted item), prefetch target <- old scratch
         b_in = b_next;
         b_next = b_sorted;
         b_sorted = t;
     }
+    if (pend_size != 0) {
+        __syncthreads();
+        store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+    }
+#ifdef VKRS_LT_TIMERS
+    if (tid == 0 && timers_out) {
+        sm.timers[10] += 1; // CTAs
+        for (int i = 0; i < 16; ++i) atomicAdd(&timers_out[i], sm.timers[i]);
+    }
+#endif
     cp_async_wait_all();
 }
 
