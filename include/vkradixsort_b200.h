@@ -1,6 +1,8 @@
 /*
- * vkradixsort_b200.h -- C-ABI of the B200-native (sm_100a) LSD radix sort that replaces
- * the VkRadixSort compute dispatches.
+ * vkradixsort_b200.h -- C-ABI of the B200-native (sm_100a) 8-bit-digit radix sort that replaces
+ * the VkRadixSort compute dispatches: the per-stage entry points and the key + payload / 64-bit / small sorts
+ * run the reference's least-significant-digit-first loop; the keys-only whole sort may run the same building
+ * blocks most-significant digit first (vkrs_set_schedule) -- every schedule returns the same bytes.
  *
  * The reference has no FFI; its seam is the C++ pass surface
  *   engine::MultiRadixSortPass  (multiradixsort/include/MultiRadixSortPass.h:7-40)
@@ -24,7 +26,10 @@
  *  - Return value: VKRS_OK or a negative vkrs_status; vkrs_last_error() gives the text.  No
  *    C++ exception crosses this boundary (the facade turns failures back into
  *    std::runtime_error as the reference throws, ComputePass.h:51-53).
- *  - A handle is not thread-safe; distinct handles on distinct streams are independent.
+ *  - A handle is not thread-safe, and it serves ONE stream at a time: its workspaces (histogram rows, piece
+ *    tables, plans cached per N) are only ordered by the stream of the call that wrote them, so before a handle
+ *    is used on another stream the caller orders that stream behind the previous call (event / stream wait).
+ *    Distinct handles on distinct streams are independent.
  */
 #ifndef VKRADIXSORT_B200_H
 #define VKRADIXSORT_B200_H
@@ -176,12 +181,35 @@ int vkrs_ipc_free(vkrs_handle handle, void *device_ptr);
 int vkrs_partition_count(vkrs_handle handle, const uint32_t *keys_in, uint32_t num_elements, uint32_t key_base,
                          uint32_t shift, int with_values, uint32_t *bucket_counts /* device, 256 x uint32 */, void *stream);
 int vkrs_partition_scatter_p2p(vkrs_handle handle, const uint32_t *keys_in, const uint32_t *values_in, uint32_t num_elements,
-                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables, void *stream);
+                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables,
+                               const uint32_t *gate /* device word, may be NULL: the kernel only works if *gate != 0 */, void *stream);
+/* The exchange's control work on the device, so that the step never returns to the host between the all-gather of the
+ * bucket counts and the local sort:
+ *   vkrs_exchange_plan   all_counts [world][256] (device, all-gathered) -> dst_tables for vkrs_partition_scatter_p2p
+ *                        (contiguous bucket ranges dealt to the ranks as evenly as the bucket granularity allows; the
+ *                        receive buffer of a rank is laid out source rank by source rank) and summary (device,
+ *                        4 + world x uint32: keys this rank receives | largest receive count of any rank | gate | 0 |
+ *                        boundaries[1 .. world-1]; gate = 1 iff the largest range fits `capacity` keys and, when
+ *                        max_imbalance_permille != 0, largest / mean load <= permille / 1000 -- pass &summary[2] as the
+ *                        gate of vkrs_partition_scatter_p2p to make the exchange conditional without a host round trip).  peer_key_ptrs / peer_value_ptrs: device arrays of the ranks'
+ *                        receive-buffer addresses as this process sees them (vkrs_ipc_open); world <= 64.
+ *   vkrs_peer_barrier    stream-ordered barrier between the ranks of one node through flags in peer memory:
+ *                        flags_local = this rank's world x uint32 flag array (vkrs_ipc_alloc, zeroed), peer_flag_ptrs =
+ *                        device array of every rank's flag array; epoch must increase by one per call on every rank. */
+int vkrs_exchange_plan(vkrs_handle handle, const uint32_t *all_counts, uint32_t world, uint32_t rank, const uint64_t *peer_key_ptrs,
+                       const uint64_t *peer_value_ptrs, uint64_t *dst_tables, uint32_t *summary, uint32_t capacity,
+                       uint32_t max_imbalance_permille, void *stream);
+int vkrs_peer_barrier(vkrs_handle handle, uint32_t *flags_local, const uint64_t *peer_flag_ptrs, uint32_t world, uint32_t rank,
+                      uint32_t epoch, void *stream);
 
 /* ---- host-buffer convenience = prepareBuffers + execute loop + verify's download
  * (MultiRadixSort.cpp:83-102): H2D of host_keys (pinned or pageable), sort on the device in
  * handle-owned buffers, D2H back into host_keys; returns after the data is back. */
 int vkrs_multi_sort_host(vkrs_handle handle, uint32_t *host_keys, uint32_t num_elements, void *stream);
+/* Device time (ms, CUDA events on `stream`) of the three stages of the last vkrs_multi_sort_host call on this handle:
+ * out3[0] = host-to-device copy, [1] = sort, [2] = device-to-host copy -- the reference times the same region around its
+ * submits only (MultiRadixSort.cpp:49-63); this is the split of the end-to-end number. */
+int vkrs_host_timings(vkrs_handle handle, double *out3);
 
 /* ---- device-side error flag (chained-scan look-back watchdog).  Synchronises `stream`,
  * returns VKRS_ERR_INTERNAL if any kernel since the last check raised the flag. ---- */
@@ -189,6 +217,7 @@ int vkrs_check_device_error(vkrs_handle handle, void *stream);
 
 /* ---- tuning hooks: pick one of the precompiled schedules / tile configurations of the keys-only
  * whole sort (also settable with the VKRS_VARIANT environment variable at create time). */
+int vkrs_resolve_schedule(vkrs_handle handle, uint32_t num_elements); /* the vkrs_schedule `auto` picks for a keys-only sort of that many keys */
 int vkrs_num_variants(void);
 const char *vkrs_variant_name(int variant);
 int vkrs_set_variant(vkrs_handle handle, int variant);

@@ -77,6 +77,8 @@ def lib() -> ctypes.CDLL:
         L.vkrs_oracle_parallel_sort.argtypes = [_u32p, ctypes.c_uint64]
         L.vkrs_oracle_num_threads.restype = ctypes.c_int
         L.vkrs_oracle_num_threads.argtypes = []
+        L.vkrs_oracle_set_num_threads.restype = None
+        L.vkrs_oracle_set_num_threads.argtypes = [ctypes.c_int]
         L.vkrs_oracle_stable_sort_pairs.restype = ctypes.c_double
         L.vkrs_oracle_stable_sort_pairs.argtypes = [_u32p, _u32p, ctypes.c_uint64]
         L.vkrs_oracle_test_sort.restype = ctypes.c_int64
@@ -180,6 +182,11 @@ def parallel_sort(keys: np.ndarray):
 
 def num_threads() -> int:
     return int(lib().vkrs_oracle_num_threads())
+
+
+def set_num_threads(threads: int) -> None:
+    """OpenMP threads of the restated shaders / parallel sort (overrides an inherited OMP_NUM_THREADS)."""
+    lib().vkrs_oracle_set_num_threads(int(threads))
 
 
 def stable_sort_pairs(keys: np.ndarray, values: np.ndarray):

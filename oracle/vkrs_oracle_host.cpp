@@ -61,6 +61,12 @@ double vkrs_oracle_parallel_sort(uint32_t *buffer, uint64_t num_elements) {
     return std::chrono::duration<double, std::milli>(end - begin).count();
 }
 
+// The OpenMP thread count, set explicitly: launchers such as torchrun export OMP_NUM_THREADS=1, which would silently
+// turn the all-host-threads reference arm of bench.py into a single-thread one.
+void vkrs_oracle_set_num_threads(int threads) {
+    if (threads > 0) omp_set_num_threads(threads);
+}
+
 int vkrs_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

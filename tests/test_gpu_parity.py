@@ -225,6 +225,52 @@ def test_pairs_are_stable(handle, dev, oracle):
         assert np.array_equal(to_host(v0), ev), (n, mx)
 
 
+def test_pairs_2e7_exact_against_stable_sort(handle, dev, oracle):
+    """BASELINE.json config 3 at a size std::stable_sort finishes in seconds: keys AND payloads bit-exact."""
+    from vkradixsort_b200 import capi
+
+    n = 20_000_000
+    keys = oracle.generate_random(n, 0x5EED0003, 0x0FFFFFFF)  # the reference's distribution; thousands of duplicates
+    keys[::7] &= np.uint32(0xFFFF)  # ... and heavy duplication in a seventh of them
+    vals = np.arange(n, dtype=np.uint32)
+    k0, v0 = to_dev(keys, dev), to_dev(vals, dev)
+    k1, v1 = scratch_like(k0), scratch_like(v0)
+    handle.multi_sort_pairs(k0, k1, v0, v1, None, capi.multi_push_constants(n, 32))
+    handle.check_device_error()
+    ek, ev = keys.copy(), vals.copy()
+    oracle.stable_sort_pairs(ek, ev)
+    assert np.array_equal(to_host(k0), ek)
+    assert np.array_equal(to_host(v0), ev)
+
+
+def test_pairs_1e8_properties(handle, dev):
+    """BASELINE.json config 3 at its stated size, 10^8 key + payload pairs, checked on the device through
+    size-independent properties: keys ascending; the payload (= original index) leads back to the key; among equal
+    keys the payloads ascend (the stable order the reference's ranking defines, multi_radixsort.comp:107-122)."""
+    from vkradixsort_b200 import capi
+
+    n = 100_000_000
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x5EED0033)
+    keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=gen)
+    keys[: n // 4] &= 0xFFFFF  # a quarter of the keys share 2^20 values: ~24 duplicates each
+    k0, v0 = keys.clone(), torch.arange(n, dtype=torch.int32, device=dev)
+    k1, v1 = torch.empty_like(k0), torch.empty_like(v0)
+    handle.multi_sort_pairs(k0, k1, v0, v1, None, capi.multi_push_constants(n, 32))
+    handle.check_device_error()
+    del k1, v1
+    flip = torch.tensor(-(1 << 31), dtype=torch.int32, device=dev)
+    o = k0 ^ flip
+    assert bool((o[1:] >= o[:-1]).all()), "keys not ascending"
+    del o
+    assert bool((keys[v0.long()] == k0).all()), "payload does not lead back to its key"
+    eq = k0[1:] == k0[:-1]
+    assert int(eq.sum()) > 1_000_000
+    assert bool((v0[1:][eq] > v0[:-1][eq]).all()), "equal keys out of input order: not stable"
+    # the payloads are a permutation of 0 .. n-1
+    assert int(v0.to(torch.int64).sum()) == n * (n - 1) // 2
+
+
 def test_staged_scatter_with_values(handle, dev, oracle):
     from vkradixsort_b200 import capi
 

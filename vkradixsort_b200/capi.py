@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "vkrs_set_profiling", "vkrs_profile_collect", "vkrs_profile_entry", "vkrs_debug_counters",
     "vkrs_launch_count", "vkrs_tile_size",
     "vkrs_set_schedule", "vkrs_get_schedule", "vkrs_schedule_name", "vkrs_bucket_stats",
-    "vkrs_debug_bucket_stop", "vkrs_set_key_span_hint",
+    "vkrs_debug_bucket_stop", "vkrs_set_key_span_hint", "vkrs_host_timings", "vkrs_resolve_schedule", "vkrs_exchange_plan", "vkrs_peer_barrier",
 ]
 
 # vkrs_schedule (include/vkradixsort_b200.h)
@@ -107,7 +107,7 @@ def load() -> ctypes.CDLL:
         "vkrs_key_range": (i32, [vp, vp, u32, vp, vp]),
         "vkrs_partition": (i32, [vp, vp, vp, vp, vp, u32, u32, u32, vp, vp]),
         "vkrs_partition_count": (i32, [vp, vp, u32, u32, u32, i32, vp, vp]),
-        "vkrs_partition_scatter_p2p": (i32, [vp, vp, vp, u32, u32, u32, vp, vp]),
+        "vkrs_partition_scatter_p2p": (i32, [vp, vp, vp, u32, u32, u32, vp, vp, vp]),
         "vkrs_ipc_alloc": (i32, [vp, u64, ctypes.POINTER(vp), ctypes.c_char_p]),
         "vkrs_ipc_open": (i32, [vp, ctypes.c_char_p, ctypes.POINTER(vp)]),
         "vkrs_ipc_close": (i32, [vp, vp]),
@@ -130,6 +130,10 @@ def load() -> ctypes.CDLL:
         "vkrs_bucket_stats": (i32, [vp, ctypes.POINTER(u32), vp]),
         "vkrs_debug_bucket_stop": (i32, [vp, i32]),
         "vkrs_set_key_span_hint": (i32, [vp, u32, u32]),
+        "vkrs_host_timings": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
+        "vkrs_resolve_schedule": (i32, [vp, u32]),
+        "vkrs_exchange_plan": (i32, [vp, vp, u32, u32, vp, vp, vp, vp, u32, u32, vp]),
+        "vkrs_peer_barrier": (i32, [vp, vp, vp, u32, u32, u32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -262,6 +266,19 @@ class Handle:
     def multi_sort_host(self, host_keys, num_elements: int, stream=None):
         self._check(self._lib.vkrs_multi_sort_host(self._h, _ptr(host_keys), num_elements, _stream(stream)))
 
+    def host_timings(self) -> dict:
+        """Device ms of the last multi_sort_host call: host-to-device copy, sort, device-to-host copy."""
+        out = (ctypes.c_double * 3)()
+        self._check(self._lib.vkrs_host_timings(self._h, out))
+        return {"h2d_ms": out[0], "sort_ms": out[1], "d2h_ms": out[2]}
+
+    def resolve_schedule(self, num_elements: int) -> int:
+        """The schedule `auto` (or the explicitly set one) runs for a keys-only sort of num_elements keys."""
+        r = self._lib.vkrs_resolve_schedule(self._h, num_elements)
+        if r < 0:
+            self._check(r)
+        return int(r)
+
     # ---- multi-GPU partition step ----
     def key_range(self, keys, num_elements: int, min_max_out, stream=None):
         self._check(self._lib.vkrs_key_range(self._h, _ptr(keys), num_elements, _ptr(min_max_out), _stream(stream)))
@@ -271,15 +288,23 @@ class Handle:
         self._check(self._lib.vkrs_partition(self._h, _ptr(keys_in), _ptr(keys_out), _ptr(values_in), _ptr(values_out),
                                              num_elements, key_base, shift, _ptr(bucket_counts), _stream(stream)))
 
+    def exchange_plan(self, all_counts, world: int, rank: int, peer_key_ptrs, peer_value_ptrs, dst_tables, summary,
+                      capacity: int = 0xFFFFFFFF, max_imbalance_permille: int = 0, stream=None):
+        self._check(self._lib.vkrs_exchange_plan(self._h, _ptr(all_counts), world, rank, _ptr(peer_key_ptrs), _ptr(peer_value_ptrs),
+                                                 _ptr(dst_tables), _ptr(summary), capacity, max_imbalance_permille, _stream(stream)))
+
+    def peer_barrier(self, flags_local, peer_flag_ptrs, world: int, rank: int, epoch: int, stream=None):
+        self._check(self._lib.vkrs_peer_barrier(self._h, _ptr(flags_local), _ptr(peer_flag_ptrs), world, rank, epoch, _stream(stream)))
+
     def partition_count(self, keys_in, num_elements: int, key_base: int, shift: int, bucket_counts, with_values=False,
                         stream=None):
         self._check(self._lib.vkrs_partition_count(self._h, _ptr(keys_in), num_elements, key_base, shift,
                                                    1 if with_values else 0, _ptr(bucket_counts), _stream(stream)))
 
     def partition_scatter_p2p(self, keys_in, num_elements: int, key_base: int, shift: int, dst_tables, values_in=None,
-                              stream=None):
+                              gate=None, stream=None):
         self._check(self._lib.vkrs_partition_scatter_p2p(self._h, _ptr(keys_in), _ptr(values_in), num_elements, key_base,
-                                                         shift, _ptr(dst_tables), _stream(stream)))
+                                                         shift, _ptr(dst_tables), _ptr(gate), _stream(stream)))
 
     def ipc_alloc(self, nbytes: int):
         """-> (device pointer, 64-byte IPC handle) of a cudaMalloc'ed buffer other ranks can map."""

@@ -6,6 +6,7 @@
 #include "../../include/vkradixsort_b200.h"
 #include "vkrs_kernels.cuh"
 #include "vkrs_msd.cuh"
+#include "vkrs_exchange.cuh"
 #include "vkrs_pipeline.cuh"
 #include "vkrs_segmented.cuh"
 
@@ -92,9 +93,11 @@ struct vkrs_context {
     // phase timers of the pipelined kernel (tuning aid; NULL unless vkrs_debug_counters was enabled)
     unsigned long long *debug_counters = nullptr;
 
-    // vkrs_multi_sort_host device buffers
+    // vkrs_multi_sort_host device buffers; events around its three stages and what they measured last (ms)
     uint32_t *host_buf[2] = {nullptr, nullptr};
     uint64_t host_cap = 0;
+    cudaEvent_t host_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double host_ms[3] = {0, 0, 0};
 
     // keys-only whole-sort schedule (vkrs_set_schedule) and the bucket schedule's workspace (vkrs_msd.cuh)
     int schedule = 0; // VKRS_SCHEDULE_AUTO
@@ -103,7 +106,7 @@ struct vkrs_context {
     uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
     int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
     uint32_t msd_first_shift = 24, msd_first_base = 0; // digit window the first histogram of the bucket schedule counts in (vkrs_set_key_span_hint)
-    uint32_t msd_local_paths = 3; // local sort: bit 0 bitmap path, bit 1 bins path (VKRS_LOCAL_PATHS, tuning / tests)
+    uint32_t msd_use_bins = 1; // local sort: 0 = per-bucket path only (VKRS_LOCAL_BINS=0, tests)
     uint32_t *msd_items = nullptr; // item_first[items + 1] | item_lo[items + 1] of the local sort
     uint64_t msd_items_cap = 0;
 };
@@ -606,7 +609,7 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
         LaunchScope scope(h, "msd_local_tile_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
                                 (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
-                                (const MsdPlan *) w.plan, h->msd_local_paths, h->debug_counters));
+                                (const MsdPlan *) w.plan, h->msd_use_bins, h->debug_counters));
     }
     if (h->msd_stop_after == 3) return VKRS_OK;
     // ---- fallback: four stable LSD passes that only work if some bucket was too large ----
@@ -759,7 +762,7 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         int iv = atoi(v);
         if (iv >= 0 && iv < NUM_VARIANTS) h->variant = iv;
     }
-    if (const char *v = getenv("VKRS_LOCAL_PATHS")) h->msd_local_paths = (uint32_t) atoi(v) & 3u;
+    if (const char *v = getenv("VKRS_LOCAL_BINS")) h->msd_use_bins = atoi(v) != 0 ? 1u : 0u;
     if (const char *v = getenv("VKRS_SCHEDULE")) {
         int iv = atoi(v);
         if (iv >= 0 && iv < VKRS_NUM_SCHEDULES) h->schedule = iv;
@@ -777,10 +780,15 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         vkrs_destroy(h);
         return r;
     }
-    if (max_num_elements_hint > 0) {
-        // smallest tile of any variant => most rows
-        const uint64_t tiles = (max_num_elements_hint + 4095) / 4096;
-        int r = ensure_status(h, tiles);
+    if (max_num_elements_hint > 0 && max_num_elements_hint < (1ull << 30)) {
+        // Everything the default schedules need for a sort of up to `hint` keys is allocated here, so that no later
+        // call has to grow a workspace (growing synchronises the device).  The tile-status arrays of the single-sweep
+        // tuning variants (56 MB for 10^8 keys) are only allocated when such a variant is selected.
+        const uint32_t n = (uint32_t) max_num_elements_hint;
+        uint32_t ctas, segments, seg_keys;
+        int r = msd_prepare(h, n, ctas, segments, seg_keys);
+        if (!r) r = grow(h, h->seg_hist, h->seg_hist_rows, (uint64_t) h->sm_count * 4, RADIX * sizeof(uint32_t), false);
+        if (!r) r = grow(h, h->msd_items, h->msd_items_cap, 2 * ((uint64_t) (n + LT_MIN_WINDOW - 1) / LT_MIN_WINDOW + 1), sizeof(uint32_t), false);
         if (r) {
             g_create_error = h->error;
             vkrs_destroy(h);
@@ -807,6 +815,8 @@ int vkrs_destroy(vkrs_handle h) {
     cudaFree(h->host_buf[1]);
     cudaFree(h->msd_ws);
     cudaFree(h->msd_items);
+    for (auto e : h->host_ev)
+        if (e) cudaEventDestroy(e);
     delete h;
     return VKRS_OK;
 }
@@ -930,7 +940,7 @@ int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
 int vkrs_set_key_span_hint(vkrs_handle h, uint32_t lo_key, uint32_t hi_key) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (lo_key > hi_key) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "lo_key > hi_key");
-    const uint32_t x = lo_key ^ hi_key;
+    const uint32_t x = hi_key - lo_key; // the span, as msd_window_kernel derives the digit window from (largest - smallest key)
     uint32_t top = 0;
     while (top < 31 && (x >> (top + 1)) != 0) ++top;
     h->msd_first_shift = top >= 15 ? top - 7 : 8;
@@ -1165,7 +1175,7 @@ int vkrs_partition_count(vkrs_handle h, const uint32_t *keys_in, uint32_t num_el
 }
 
 int vkrs_partition_scatter_p2p(vkrs_handle h, const uint32_t *keys_in, const uint32_t *values_in, uint32_t num_elements,
-                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables, void *stream) {
+                               uint32_t key_base, uint32_t shift, const uint64_t *dst_tables, const uint32_t *gate, void *stream) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (num_elements == 0) return VKRS_OK;
     if (num_elements >= (1u << 30)) return fail(h, VKRS_ERR_UNSUPPORTED, "at most 2^30-1 keys per call");
@@ -1175,9 +1185,41 @@ int vkrs_partition_scatter_p2p(vkrs_handle h, const uint32_t *keys_in, const uin
     const unsigned long long *tables = reinterpret_cast<const unsigned long long *>(dst_tables);
     if (values_in)
         return launch_seg_t<uint32_t, true, PAIR_WORKERS, PAIR_KPT, 2, 1, true, true>(h, keys_in, nullptr, values_in, nullptr, num_elements,
-                                                                                      shift, s, key_base, nullptr, false, true, tables);
+                                                                                      shift, s, key_base, nullptr, false, true, tables, gate);
     return launch_seg_t<uint32_t, false, 384, 16, 2, 1, true, true>(h, keys_in, nullptr, nullptr, nullptr, num_elements, shift, s,
-                                                                    key_base, nullptr, false, true, tables);
+                                                                    key_base, nullptr, false, true, tables, gate);
+}
+
+int vkrs_exchange_plan(vkrs_handle h, const uint32_t *all_counts, uint32_t world, uint32_t rank, const uint64_t *peer_key_ptrs,
+                       const uint64_t *peer_value_ptrs, uint64_t *dst_tables, uint32_t *summary, uint32_t capacity,
+                       uint32_t max_imbalance_permille, void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!all_counts || !peer_key_ptrs || !dst_tables || !summary) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (world == 0 || world > (uint32_t) EXCHANGE_MAX_RANKS || rank >= world)
+        return fail(h, VKRS_ERR_INVALID_ARGUMENT, "world=%u rank=%u: at most %d ranks", world, rank, EXCHANGE_MAX_RANKS);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LaunchScope scope(h, "exchange_plan_kernel", s);
+    exchange_plan_kernel<<<1, RADIX, 0, s>>>(all_counts, world, rank, reinterpret_cast<const unsigned long long *>(peer_key_ptrs),
+                                             reinterpret_cast<const unsigned long long *>(peer_value_ptrs),
+                                             reinterpret_cast<unsigned long long *>(dst_tables), summary, capacity, max_imbalance_permille);
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
+}
+
+int vkrs_peer_barrier(vkrs_handle h, uint32_t *flags_local, const uint64_t *peer_flag_ptrs, uint32_t world, uint32_t rank, uint32_t epoch,
+                      void *stream) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    if (!flags_local || !peer_flag_ptrs) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (world == 0 || world > (uint32_t) EXCHANGE_MAX_RANKS || rank >= world)
+        return fail(h, VKRS_ERR_INVALID_ARGUMENT, "world=%u rank=%u: at most %d ranks", world, rank, EXCHANGE_MAX_RANKS);
+    DeviceGuard guard(h->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    LaunchScope scope(h, "peer_signal_wait_kernel", s);
+    peer_signal_wait_kernel<<<1, EXCHANGE_MAX_RANKS, 0, s>>>(flags_local, reinterpret_cast<const unsigned long long *>(peer_flag_ptrs), world, rank,
+                                                             epoch);
+    VKRS_CUDA(h, cudaGetLastError());
+    return VKRS_OK;
 }
 
 int vkrs_ipc_alloc(vkrs_handle h, uint64_t bytes, void **device_ptr, unsigned char *ipc_handle_64) {
@@ -1271,13 +1313,35 @@ int vkrs_multi_sort_host(vkrs_handle h, uint32_t *host_keys, uint32_t num_elemen
         if (r) return r;
         h->host_cap = num_elements;
     }
+    if (!h->host_ev[0])
+        for (auto &e : h->host_ev) VKRS_CUDA(h, cudaEventCreate(&e));
     const size_t bytes = (size_t) num_elements * sizeof(uint32_t);
+    VKRS_CUDA(h, cudaEventRecord(h->host_ev[0], s));
     VKRS_CUDA(h, cudaMemcpyAsync(h->host_buf[0], host_keys, bytes, cudaMemcpyHostToDevice, s));
+    VKRS_CUDA(h, cudaEventRecord(h->host_ev[1], s));
     int r = vkrs_sort_auto(h, h->host_buf[0], h->host_buf[1], num_elements, stream);
     if (r) return r;
+    VKRS_CUDA(h, cudaEventRecord(h->host_ev[2], s));
     VKRS_CUDA(h, cudaMemcpyAsync(host_keys, h->host_buf[0], bytes, cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaEventRecord(h->host_ev[3], s));
     VKRS_CUDA(h, cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        VKRS_CUDA(h, cudaEventElapsedTime(&ms, h->host_ev[i], h->host_ev[i + 1]));
+        h->host_ms[i] = ms;
+    }
     return VKRS_OK;
+}
+
+int vkrs_host_timings(vkrs_handle h, double *out3) {
+    if (!h || !out3) return VKRS_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < 3; ++i) out3[i] = h->host_ms[i];
+    return VKRS_OK;
+}
+
+int vkrs_resolve_schedule(vkrs_handle h, uint32_t num_elements) {
+    if (!h) return VKRS_ERR_INVALID_ARGUMENT;
+    return resolve_schedule(h, num_elements);
 }
 
 } // extern "C"

@@ -579,21 +579,18 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 // item is sorted by the full key, which is the same thing because its buckets already are in order.
 //
 // msd_local_tile_kernel, one CTA per item at a time; the item's keys were copied into shared memory
-// with cp.async while the previous item was being sorted (three key buffers rotate through the roles
-// "keys", "sorted", "copy target").  Three ways to sort an item, tried in this order:
-//   bitmap   when the item's key span is at most 2^17 values (always, for 10^8 uniform keys): value v is
-//            bit v of a bitmap; a second bit plane takes the second copy of a value.  One atomicOr per
-//            key, a popcount scan over the 4096 words, and a key's final place is
-//            prefix[word] + popc(bits below it) -- exact, nothing to fix up.  A value held three
-//            times or more sends the item to the next path.
-//   bins     an order-preserving map of the key span onto 4096 bins, (key - base) >> s; one atomic to
-//            count, a scan, one atomic to place; then position p ranks its key among the (few) keys of
-//            its bin by comparison.  A bin above LT_BIN_LIMIT keys sends the item on.
+// with cp.async while the previous item was being sorted, and the sorted item goes back to the array while
+// the next one is being counted (three key buffers rotate through the roles "this item's keys, then its
+// sorted keys", "keys grouped by bin / the previous item on its way out", "copy target").  Two ways to sort an item:
+//   bins     an order-preserving map of the item's key span onto LT_BINS bins, umulhi(key - base, mult) -- a
+//            multiplier, not a shift, so that every bin is used whatever the span; one atomic per key to count,
+//            a conflict-free 128-bit scan, one atomic to place; then position p ranks its key among the (few) keys
+//            of its bin by comparison (local_tile_bins).  A bin of LT_BIN_LIMIT keys or more sends the item on.
 //   buckets  the item's buckets one by one, two 8-bit passes in shared memory (local_bucket_sort): byte 0
 //            unstable with atomics, byte 1 stable with the warp-private ballot ranking of the digit pass
 //            (vkrs_tile.cuh / multi_radixsort.comp:97-122).  Always correct, several times slower.
 // Nothing is written to global memory before a path has succeeded; the sorted item then goes back in
-// place, fully coalesced.
+// place with 128-bit stores.
 // =====================================================================================
 #ifndef VKRS_LT_CAP
 #define VKRS_LT_CAP 6144
@@ -1064,7 +1061,7 @@ template <int XF>
 __global__ void __launch_bounds__(LT_THREADS, VKRS_LT_MIN_BLOCKS)
 msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start,
                       const uint32_t *__restrict__ item_first, const uint32_t *__restrict__ item_lo, uint32_t n,
-                      const MsdPlan *__restrict__ plan, uint32_t paths /* bit 1 clear: bucket path only (tests) */,
+                      const MsdPlan *__restrict__ plan, uint32_t use_bins /* 0: per-bucket path only (tests) */,
                       unsigned long long *__restrict__ timers_out) {
     extern __shared__ __align__(128) unsigned char smem_raw_tile[];
     LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_tile);
@@ -1079,7 +1076,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     }
     if (tid == 0) {
         sm.params[0] = plan->base; // bucket j holds the keys base + (j << low_bits) + [0, 2^low_bits)
-        sm.params[1] = paths;
+        sm.params[1] = use_bins;
     }
     const uint32_t window = lt_window(plan->max_sub);
     const uint32_t num_items = (n + window - 1) / window;
@@ -1131,7 +1128,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                 // the item's buckets are j0 .. j1-1 and a key of bucket j is kbase + (j << low_bits) + its low bits
                 const uint32_t base = sm.params[0] + (j0 << low_bits);
                 uint32_t *in = sm.buf[b_in] + (lo & 3u);
-                if ((sm.params[1] & 2u) && size <= (uint32_t) LT_CAP - 4u) {
+                if (sm.params[1] != 0 && size <= (uint32_t) LT_CAP - 4u) {
                     const uint32_t mult = sm.params[2 + mslot];
                     const bool exact = mult == 0;
                     todo = local_tile_bins(sm, in, sm.buf[b_sorted], sm.buf[b_in], lo & 3u, size, exact ? base - 1u : base, exact ? 0xFFFFFFFFu : mult, exact);

@@ -85,14 +85,16 @@ def plan_exchange(all_counts: np.ndarray, rank: int) -> ExchangePlan:
     cum = np.cumsum(per_bucket)
     boundaries = [0]
     for r in range(1, world):
-        target = total * r / world
         b = 0
         if total > 0:
-            idx = int(np.searchsorted(cum, target, side="left"))  # first bucket whose running total reaches the target
+            # first bucket whose running total reaches total * r / world -- in integers, exactly as the device-side
+            # plan (vkrs_exchange.cuh: exchange_plan_kernel) computes it
+            tr = total * r
+            idx = int(np.searchsorted(cum * world, tr, side="left"))
             idx = min(idx, NUM_BUCKETS - 1)
             before = int(cum[idx - 1]) if idx > 0 else 0
             # cut before or after that bucket, whichever lands closer to the target
-            b = idx if (target - before) <= (int(cum[idx]) - target) else idx + 1
+            b = idx if (tr - before * world) <= (int(cum[idx]) * world - tr) else idx + 1
         boundaries.append(min(NUM_BUCKETS, max(boundaries[-1], b)))  # monotone; empty ranges are allowed
     boundaries.append(NUM_BUCKETS)
     send = [int(all_counts[rank, boundaries[d]:boundaries[d + 1]].sum()) for d in range(world)]
@@ -128,8 +130,8 @@ class DeviceOps:
         self.handle.partition_count(keys_in, n, key_base, shift, self.counts, with_values)
         return self.counts
 
-    def partition_scatter_p2p(self, keys_in, n, key_base, shift, dst_tables, values_in=None):
-        self.handle.partition_scatter_p2p(keys_in, n, key_base, shift, dst_tables, values_in)
+    def partition_scatter_p2p(self, keys_in, n, key_base, shift, dst_tables, values_in=None, gate=None):
+        self.handle.partition_scatter_p2p(keys_in, n, key_base, shift, dst_tables, values_in, gate)
 
     def local_sort(self, buf0, buf1, n, val0=None, val1=None, key_span=None):
         """key_span = (lo, hi): the key range this rank owns after the exchange (a hint for the local sort)."""
@@ -166,7 +168,15 @@ class DistributedSorter:
         self.pairs = pairs
         self.p2p = (ops is None and world > 1) if p2p is None else p2p
         self.capacity = int(n_local * slack) + 1024
+        if world > 1 and dist.is_initialized():
+            # every rank must size (and later re-size) its receive buffers identically: decisions that depend on the
+            # capacity are taken without communication
+            t = torch.tensor([self.capacity], dtype=torch.int64, device=device if dist.get_backend(group) == "nccl" else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            self.capacity = int(t.item())
         self.last_plan: ExchangePlan | None = None
+        self._epoch = 0
+        self._speculate = False  # the device-planned exchange is used once a host-planned sort has shown that the top-byte buckets balance
         self.exchange_bytes = 0
         self.used_p2p = False
         self.used_key_range = False
@@ -181,36 +191,55 @@ class DistributedSorter:
         if self.p2p:
             self._alloc_p2p()
 
-    def _alloc_p2p(self):
-        """Receive buffers every rank of the node can store into: cudaMalloc + CUDA IPC, wrapped as
-        torch tensors for the local sort."""
+    def _share(self, nbytes):
+        """cudaMalloc + CUDA IPC: a buffer of this rank every rank of the node can store into.  Returns
+        (own pointer, [the buffer of rank r as this process sees it])."""
         torch, dist = self.torch, self.dist
+        ptr, hd = self.handle.ipc_alloc(nbytes)
+        self._ipc_owned.append(ptr)
+        mine = torch.frombuffer(bytearray(hd), dtype=torch.uint8).to(self.device)
+        everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        handles = everyone.cpu().numpy().tobytes()
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(ptr)
+            else:
+                p = self.handle.ipc_open(handles[64 * r:64 * (r + 1)])
+                self._ipc_opened.append(p)
+                ptrs.append(p)
+        return ptr, ptrs
+
+    def _alloc_p2p(self):
+        """Receive buffers (and the flag array of the peer barrier) every rank of the node can store into, wrapped as
+        torch tensors for the local sort.  Collective: every rank calls it at the same point."""
+        torch = self.torch
         self._release_p2p()
-        nbytes = 4 * self.capacity
-        self.peer_ptrs = []
+        self.peer_ptrs, self.peer_ptrs_dev = [], []
         for which in range(2 if self.pairs else 1):  # keys, payloads
-            ptr, hd = self.handle.ipc_alloc(nbytes)
-            self._ipc_owned.append(ptr)
-            mine = torch.frombuffer(bytearray(hd), dtype=torch.uint8).to(self.device)
-            everyone = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(everyone, mine, group=self.group)
-            handles = everyone.cpu().numpy().tobytes()
-            ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(ptr)
-                else:
-                    p = self.handle.ipc_open(handles[64 * r:64 * (r + 1)])
-                    self._ipc_opened.append(p)
-                    ptrs.append(p)
+            ptr, ptrs = self._share(4 * self.capacity)
             self.peer_ptrs.append(ptrs)
+            self.peer_ptrs_dev.append(torch.tensor(ptrs, dtype=torch.int64, device=self.device))
             t = _tensor_from_pointer(torch, ptr, self.capacity, self.device)
             if which == 0:
                 self.recv[0] = t
             else:
                 self.recv_vals[0] = t
-        self.dst_tables = torch.zeros(4 * NUM_BUCKETS, dtype=torch.int64, device=self.device)
-        self._dst_host = torch.zeros(4 * NUM_BUCKETS, dtype=torch.int64).pin_memory()
+        fptr, fptrs = self._share(4 * 64)
+        self.flags = _tensor_from_pointer(torch, fptr, 64, self.device)
+        self.flags.zero_()
+        self.peer_flags_dev = torch.tensor(fptrs, dtype=torch.int64, device=self.device)
+        self._epoch = 0
+        torch.cuda.synchronize()
+        self.dist.barrier(group=self.group)  # every flag array is zero before anybody signals
+        if not hasattr(self, "_gathered"):  # (kept across re-allocations: a sort in progress holds its counts here)
+            self.dst_tables = torch.zeros(4 * NUM_BUCKETS, dtype=torch.int64, device=self.device)
+            self.summary = torch.zeros(4 + 64, dtype=torch.int32, device=self.device)
+            self._gathered = torch.zeros(self.world * NUM_BUCKETS, dtype=torch.int32, device=self.device)
+            self._counts_host = torch.zeros(self.world * NUM_BUCKETS, dtype=torch.int32).pin_memory()
+            self._summary_host = torch.zeros(4 + 64, dtype=torch.int32).pin_memory()
+            self._counts_event = torch.cuda.Event()
 
     def _release_p2p(self):
         if self._ipc_opened or self._ipc_owned:
@@ -250,53 +279,77 @@ class DistributedSorter:
             # local sort, so the receive buffers are free to be overwritten.
             if self.p2p:
                 counts = self.ops.partition_count(keys, n, key_base, shift, values is not None)
+                gathered = self._gathered
             else:
                 counts = self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
-            gathered = torch.empty(self.world * NUM_BUCKETS, dtype=counts.dtype, device=counts.device)
+                gathered = torch.empty(self.world * NUM_BUCKETS, dtype=counts.dtype, device=counts.device)
             dist.all_gather_into_tensor(gathered, counts, group=self.group)
-            return gathered.view(self.world, NUM_BUCKETS).cpu().numpy()
+            return gathered
+
+        def fused_exchange(gathered, key_base, shift, gate):
+            """plan on the device -> partition kernel that stores into the owners' receive buffers -> peer barrier;
+            nothing here waits for the host.  gate: the plan kernel decides whether the scatter runs (balance, capacity)
+            and the decision is copied to the host between the two kernels."""
+            self.handle.exchange_plan(gathered, self.world, self.rank, self.peer_ptrs_dev[0],
+                                      self.peer_ptrs_dev[1] if values is not None else None, self.dst_tables, self.summary,
+                                      self.capacity, int(round(self.max_imbalance * 1000)) if gate else 0)
+            if gate:
+                self._summary_host.copy_(self.summary, non_blocking=True)
+                self._counts_event.record()
+            self.ops.partition_scatter_p2p(keys, n, key_base, shift, self.dst_tables, values, self.summary[2:3] if gate else None)
+            self._epoch += 1
+            self.handle.peer_barrier(self.flags, self.peer_flags_dev, self.world, self.rank, self._epoch)
 
         # 1+2+3. Speculate that the keys use the full 32-bit range: bucket = top byte is valid for ANY
         # input (it only may balance badly), and it saves the key-range pass and one host round trip.
         key_base, shift = 0, 24
-        all_counts = count_and_gather(key_base, shift)
         self.used_key_range = False
-        if plan_exchange(all_counts, self.rank).imbalance > self.max_imbalance:
+        gathered = count_and_gather(key_base, shift)
+        speculated = False
+        if self.p2p and self._speculate:
+            # The last sort balanced with the top-byte buckets and fitted the buffers: run the whole exchange on the
+            # device right away and look at the counts on the host WHILE it runs.  The plan kernel itself closes the
+            # gate of the scatter if this input does not balance or would overflow a receive buffer (every rank
+            # sees the same counts, so every rank takes the same decision); then the host-planned path below repeats it.
+            self._counts_host.copy_(gathered, non_blocking=True)
+            fused_exchange(gathered, key_base, shift, gate=True)
+            self._counts_event.synchronize()  # counts and the plan kernel's verdict are on the host; the scatter is running
+            all_counts = self._counts_host.numpy().reshape(self.world, NUM_BUCKETS).astype(np.int64)
+            speculated = int(self._summary_host[2]) != 0  # closed on every rank alike: nothing has been stored anywhere
+            self._speculate = speculated
+        else:
+            all_counts = gathered.view(self.world, NUM_BUCKETS).cpu().numpy()
+        plan = plan_exchange(all_counts, self.rank)
+        largest = max(int(all_counts[:, plan.boundaries[r]:plan.boundaries[r + 1]].sum()) for r in range(self.world))
+        if not speculated and plan.imbalance > self.max_imbalance:
             # narrow or skewed keys: map the OCCUPIED range onto the 256 buckets and count again
             mm = self.ops.key_range(keys, n)
             t = torch.stack([mm[0], -mm[1]])
             dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
             kmin, neg_kmax = (int(x) for x in t.tolist())
             key_base, shift = choose_bucket_map(kmin, -neg_kmax)
-            all_counts = count_and_gather(key_base, shift)
+            all_counts = count_and_gather(key_base, shift).view(self.world, NUM_BUCKETS).cpu().numpy()
             self.used_key_range = True
-        plan = plan_exchange(all_counts, self.rank)
+            plan = plan_exchange(all_counts, self.rank)
+            largest = max(int(all_counts[:, plan.boundaries[r]:plan.boundaries[r + 1]].sum()) for r in range(self.world))
         self.last_plan = plan
         total_recv = sum(plan.recv_counts)
         self.exchange_bytes = 4 * (n - plan.send_counts[self.rank]) * (2 if values is not None else 1)
-        largest = max(int(all_counts[:, plan.boundaries[r]:plan.boundaries[r + 1]].sum()) for r in range(self.world))
-        fused = self.p2p and largest <= self.capacity  # every rank takes the same decision
+        if largest > self.capacity:
+            # `largest` and `capacity` are the same numbers on every rank: the re-allocation (a collective when the
+            # buffers are shared between the ranks) is entered by all of them together
+            self._ensure(largest)
+        fused = self.p2p
         self.used_p2p = fused
-        if not fused:
-            self._ensure(total_recv)
         recv = self.recv[0][:total_recv]
         recv_v = self.recv_vals[0][:total_recv] if values is not None else None
 
         # 4. exchange
         if fused:
-            owner, offset, first, end = destination_offsets(all_counts, plan.boundaries, self.rank)
-            tab = self._dst_host.numpy()
-            for which in range(2 if values is not None else 1):
-                base = np.array(self.peer_ptrs[which], dtype=np.int64)[owner]
-                tab[which * NUM_BUCKETS:(which + 1) * NUM_BUCKETS] = base + 4 * offset
-            tab[2 * NUM_BUCKETS:3 * NUM_BUCKETS] = first
-            tab[3 * NUM_BUCKETS:4 * NUM_BUCKETS] = end
-            self.dst_tables.copy_(self._dst_host, non_blocking=True)
-            self.ops.partition_scatter_p2p(keys, n, key_base, shift, self.dst_tables, values)
-            dist.barrier(group=self.group)  # every rank's stores have landed before anybody sorts
+            if not speculated:
+                fused_exchange(self._gathered, key_base, shift, gate=False)  # the counts of the bucket map that was settled on
+                self._speculate = not self.used_key_range
         else:
-            if self.p2p:  # overflow fallback: the staged path still needs the partitioned array
-                self.ops.partition(keys, scratch, n, key_base, shift, values, values_scratch)
             dist.all_to_all_single(recv, scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
             if values is not None:
                 dist.all_to_all_single(recv_v, values_scratch[:n], plan.recv_counts, plan.send_counts, group=self.group)
