@@ -387,7 +387,7 @@ int launch_global_histogram(vkrs_context *h, const KeyT *keys, uint32_t n, cudaS
 // ---- the bucket schedule (vkrs_msd.cuh) -------------------------------------------------------
 #ifndef VKRS_MSD_WORKERS
 #define VKRS_MSD_WORKERS 384
-#define VKRS_MSD_KPT 16
+#define VKRS_MSD_KPT 20
 #define VKRS_MSD_GROUPS 2
 #endif
 #ifndef VKRS_MSD_UNIFORM_FAST

@@ -26,7 +26,6 @@ exchange_plan_kernel(const uint32_t *__restrict__ counts, uint32_t world, uint32
                      const unsigned long long *__restrict__ peer_vals, unsigned long long *__restrict__ dst_tables,
                      uint32_t *__restrict__ summary, uint32_t capacity, uint32_t max_imbalance_permille) {
     __shared__ unsigned long long cum[RADIX];       // inclusive running total over the buckets, all ranks
-    __shared__ uint32_t below[RADIX];               // keys of the lower source ranks in bucket b
     __shared__ uint32_t bounds[EXCHANGE_MAX_RANKS + 1];
     __shared__ unsigned long long part[EXCHANGE_MAX_RANKS + 1];
     __shared__ uint32_t scratch[8];
@@ -37,7 +36,7 @@ exchange_plan_kernel(const uint32_t *__restrict__ counts, uint32_t world, uint32
         if (s < rank) low += c;
         total_b += c;
     }
-    below[b] = low;
+
     // inclusive scan of the bucket totals (64-bit: up to 64 x 2^30 keys)
     {
         const int lane = b & 31, warp = b >> 5;
