@@ -255,10 +255,12 @@ const char *vkrs_schedule_name(int schedule);
  * rank's key range after the multi-GPU exchange).  The schedule finds the occupied key range by itself; with
  * the hint its first histogram is already counted in the right digit window, which saves one 4 B/key recount.  A wrong hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint. */
 int vkrs_set_key_span_hint(vkrs_handle handle, uint32_t lo_key, uint32_t hi_key);
-/* Control words of the handle's last BUCKET sort, for tests and diagnostics: out8 = {shift of pass 1,
+/* Control words of the handle's last BUCKET sort, for tests and diagnostics: out16 = {shift of pass 1,
  * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, smallest key,
- * largest bucket pass 2 saw, pieces of pass 1, pieces of pass 2}.  Synchronises `stream`. */
-int vkrs_bucket_stats(vkrs_handle handle, uint32_t *out8, void *stream);
+ * largest bucket the shared-memory sort saw, pieces of pass 1, pieces of pass 2, largest key, 0, base of the digit
+ * window, buckets finished by counting ("big" buckets: above 4096 keys), their histogram work items, 0, 0, 0}.
+ * Synchronises `stream`. */
+int vkrs_bucket_stats(vkrs_handle handle, uint32_t *out16, void *stream);
 /* Test aid: end the BUCKET schedule after stage 1 (partition pass 1: keys grouped by the top digit, in
  * buf1), 2 (pass 2: grouped by the top two digits, in buf0) or 3 (local sort, fallback passes not
  * enqueued) so that every stage can be compared with the oracle; 0 = whole schedule (default). */

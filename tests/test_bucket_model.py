@@ -1,6 +1,6 @@
 """CPU tests of the bucket schedule's logic through its numpy model (oracle/bucket_model.py): the digit window on
-the occupied key range, the recount rule, the two fallback rules, the item windows and the bin map + fix-up of
-the local sort -- against std::sort order (MultiRadixSort::testSort, multiradixsort/src/MultiRadixSort.cpp:148-161).
+the occupied key range, the recount rule, the big-bucket (counting) and fallback rules, the item windows and the bin map
++ fix-up of the local sort -- against std::sort order (MultiRadixSort::testSort, multiradixsort/src/MultiRadixSort.cpp:148-161).
 The same inputs and the same expected control words are asserted on the device in tests/test_gpu_bucket.py."""
 import numpy as np
 import pytest
@@ -41,7 +41,7 @@ def test_digit_window_and_recount(oracle):
     n = 100_003
     # full-range keys: counted at (0, 24) from the start, nothing to redo
     _, p = M.sort(oracle.generate_random(n, 1, 0xFFFFFFFF))
-    assert (p.base, p.shift1, p.shift2, p.recount, p.fallback) == (0, 24, 16, False, False)
+    assert (p.base, p.shift1, p.shift2, p.recount, p.fallback, p.big_buckets) == (0, 24, 16, False, False, 0)
     # the reference's 28-bit keys: the window moves under bit 27, the first histogram is counted again
     keys = oracle.generate_random(n, 2, 0x0FFFFFFF)
     _, p = M.sort(keys)
@@ -65,30 +65,47 @@ def test_digit_window_and_recount(oracle):
     assert (p.shift2, p.fallback) == (0, False) and np.array_equal(out, np.sort(mapped))
 
 
-def test_fallback_rules(oracle):
+def test_big_bucket_and_fallback_rules(oracle):
     rng = np.random.default_rng(7)
     n = 300_000
-    # four 16-bit-prefix buckets of 75,000 keys: pass 2 sees the overflow
+    # four 16-bit-prefix buckets of 75,000 keys: too large for shared memory, sorted by counting -- no fallback
     keys = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
     out, p = M.sort(keys)
-    assert p.fallback and not p.skip_pass2 and p.max_bucket > M.LOCAL_MAX and p.shift1 == 24
+    assert not p.fallback and p.big_buckets == 4 and p.shift1 == 24, p
     assert np.array_equal(out, np.sort(keys))
-    # a top-digit bucket above 256 * 4096 keys: pass 1 already knows, pass 2 is skipped
+    # half of the keys under one prefix, the rest uniform: one big bucket, its neighbours' item goes bucket by bucket
+    m = 400_000
+    keys = np.where(rng.random(m) < 0.5, np.uint32(0x2BCD0000) | rng.integers(0, 1 << 16, m, dtype=np.uint32),
+                    rng.integers(0, 1 << 32, m, dtype=np.uint64).astype(np.uint32)).astype(np.uint32)
+    out, p = M.sort(keys, fix_up_limit=0)
+    assert not p.fallback and p.big_buckets == 1 and p.redo_items >= 1 and p.max_bucket < 100, p
+    assert np.array_equal(out, np.sort(keys))
+    # 512 buckets of ~5,900 keys: more than the 256 the counter pool takes at 16 low bits -> the LSD passes
     m = 3_000_000
     keys = ((rng.integers(0, 2, m, dtype=np.uint32) * np.uint32(0xFF000000)) | rng.integers(0, 1 << 24, m, dtype=np.uint32)).astype(np.uint32)
     out, p = M.sort(keys)
-    assert p.fallback and p.skip_pass2 and p.max_bucket == 0 and p.shift1 == 24
+    assert p.fallback and p.big_buckets == 512 and p.shift1 == 24, p
     assert np.array_equal(out, np.sort(keys))
-    # uniform keys never fall back below 2.2e8 keys: the largest of 65536 buckets stays far below 4096
+    # uniform keys never get there below 2.2e8 keys: the largest of 65536 buckets stays far below 4096
     _, p = M.sort(oracle.generate_random(2_000_003, 5, 0xFFFFFFFF))
-    assert not p.fallback and p.max_bucket < 100
+    assert not p.fallback and p.big_buckets == 0 and p.max_bucket < 100
 
 
-def test_item_windows():
-    assert M.lt_window(0) == 4096 and M.lt_window(1716) == 4096 and M.lt_window(2048) == 4096
-    assert M.lt_window(2049) == 2048 and M.lt_window(4096) == 2048 and M.lt_window(5000) == 1024
-    assert M.lt_window(6000) == 256  # cannot fit: such items go to the per-bucket path
+def test_item_windows_and_bin_map():
+    assert M.lt_window(0) == 7164 & ~511 == 6656 and M.lt_window(1716) == 5120 and M.lt_window(2044) == 5120
+    assert M.lt_window(2045) == 4608 and M.lt_window(4096) == 2560 and M.lt_window(5000) == 2048
+    assert M.lt_window(7000) == 256  # cannot fit: such items go to the per-bucket path
     assert M.hint_window(0, 0xFFFFFFFF) == (0, 24) and M.hint_window(0xC0000000, 0xFFFFFFFF) == (0xC0000000, 22)
+    assert M.hint_window(0x60000000, 0x9FFFFFFF) == (0x60000000, 22)  # the span decides, not the differing bits
+    # the multiplicative bin map uses all bins whatever the span, stays below LT_BINS and is monotone
+    for nb, low_bits in ((1, 16), (3, 16), (5, 16), (700, 8), (65536, 16), (1, 13), (2, 12)):
+        span = nb << low_bits
+        mult = M.bin_mult(nb, low_bits)
+        x = np.unique(np.concatenate([np.arange(0, min(span, 5000)), np.linspace(0, span - 1, 5000).astype(np.int64), [span - 1]]))
+        bins = (x * mult) >> 32
+        assert bins.max() < M.LT_BINS and np.all(np.diff(bins) >= 0)
+        assert bins.max() >= M.LT_BINS - 2, (nb, low_bits, int(bins.max()))
+    assert M.bin_mult(1, 12) == 0 and M.bin_mult(16, 8) == 0  # the span fits the bins: exact mode
 
 
 def test_model_property_random_masks_and_offsets():

@@ -123,27 +123,59 @@ def test_bucket_stages(handle, dev, oracle):
         assert oracle.test_sort(np.sort(keys), b0) == -1, f"{name}: local sort"
 
 
+def test_big_buckets_are_counted_not_sorted(handle, dev, oracle):
+    """A 16-bit-prefix bucket above 4096 keys cannot be finished in shared memory.  All its keys agree above the low
+    16 bits, so it is sorted by counting (histogram of the low bits, scan, fill) whatever its size -- no whole-array
+    fallback for skewed keys."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(7)
+    n = 300_000
+    cases = {
+        # four 16-bit-prefix buckets of 75,000 keys each
+        "four_prefixes": ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32),
+        # half of the keys under one 16-bit prefix, the rest uniform
+        "hot_prefix": np.where(rng.random(2_000_003) < 0.5, np.uint32(0x2BCD0000) | rng.integers(0, 1 << 16, 2_000_003, dtype=np.uint32),
+                               rng.integers(0, 1 << 32, 2_000_003, dtype=np.uint64).astype(np.uint32)).astype(np.uint32),
+        # two narrow clusters far apart (bell-shaped, heavy duplicates inside)
+        "two_clusters": np.concatenate([(0x20000000 + rng.normal(0, 3000, 700_000)).astype(np.int64),
+                                        (0xD0000000 + rng.normal(0, 40000, 800_000)).astype(np.int64)]).astype(np.uint32),
+        # one giant bucket spanning several histogram work items, few distinct low values (same-address atomics)
+        "giant_few_values": np.concatenate([(np.uint32(0x77770000) | (rng.integers(0, 5, 1_500_000, dtype=np.uint32) * np.uint32(13001))).astype(np.uint32),
+                                            np.array([3, 0xFFFFFF00], dtype=np.uint32)]),
+    }
+    cases["two_clusters"] = rng.permutation(cases["two_clusters"])
+    for name, keys in cases.items():
+        out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+        st = handle.bucket_stats()
+        assert np.array_equal(out, np.sort(keys)), (name, st)
+        assert st["fallback"] == 0 and st["big_buckets"] >= 1, (name, st)
+        # ... and the counters are clean for the next sort on this handle
+        out, _ = run_sort(handle, keys[::-1].copy(), dev, capi.SCHEDULE_BUCKET)
+        assert np.array_equal(out, np.sort(keys)), (name, "second sort")
+    st = handle.bucket_stats()
+
+
 def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
-    """A 16-bit-prefix bucket above 4096 keys cannot be finished in shared memory: the device raises
-    the fallback word and the stable LSD passes behind the schedule sort the array."""
+    """More big buckets than the counting path takes (256 at 16 low bits): the device raises the fallback word and
+    the stable LSD passes behind the schedule sort the array."""
     from vkradixsort_b200 import capi
 
     n = 300_000
     rng = np.random.default_rng(7)
-    # four 16-bit-prefix buckets of 75,000 keys each
-    keys = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
-    out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
-    st = handle.bucket_stats()
-    assert st["fallback"] == 1 and st["max_bucket"] > 4096 and st["shift1"] == 24, st
-    assert np.array_equal(out, np.sort(keys))
-    # a top-digit bucket above 256 * 4096 keys must overflow: pass 1 notices, pass 2 is not even run
-    # (max_bucket is only gathered by pass 2), the LSD passes sort the untouched input
+    # 512 16-bit-prefix buckets of ~5,900 keys each
     m = 3_000_000
     keys0 = ((rng.integers(0, 2, m, dtype=np.uint32) * np.uint32(0xFF000000)) | rng.integers(0, 1 << 24, m, dtype=np.uint32)).astype(np.uint32)
     out0, _ = run_sort(handle, keys0, dev, capi.SCHEDULE_BUCKET)
     st = handle.bucket_stats()
-    assert st["fallback"] == 1 and st["max_bucket"] == 0 and st["shift1"] == 24, st
+    assert st["fallback"] == 1 and st["big_buckets"] > 256 and st["shift1"] == 24, st
     assert np.array_equal(out0, np.sort(keys0))
+    # the next sort on the handle is not disturbed by the unfinished counting
+    keys9 = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
+    out9, _ = run_sort(handle, keys9, dev, capi.SCHEDULE_BUCKET)
+    st = handle.bucket_stats()
+    assert st["fallback"] == 0 and st["big_buckets"] == 4, st
+    assert np.array_equal(out9, np.sort(keys9))
     # only the occupied key range is sort work: the digit window sits on (key - smallest key), two passes finish the job
     keys1 = (np.uint32(0x12340000) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)
     out1, _ = run_sort(handle, keys1, dev, capi.SCHEDULE_BUCKET)
@@ -219,9 +251,14 @@ def test_typed_keys_through_the_bucket_schedule(handle, dev, oracle):
         assert np.array_equal(sort_typed(small, capi.KEY_I32, schedule), np.sort(small)), (n, "int32 in [-100, 100]")
         st = handle.bucket_stats()
         assert st["fallback"] == 0 and st["shift2"] == 0, st
-        hot = np.where(rng.random(n) < 0.5, np.int32(5), ints).astype(np.int32)  # half of the keys equal: the fallback passes undo the map
+        hot = np.where(rng.random(n) < 0.5, np.int32(5), ints).astype(np.int32)  # half of the keys equal: one bucket is finished by counting, its fill undoes the map
         assert np.array_equal(sort_typed(hot, capi.KEY_I32, schedule), np.sort(hot)), (n, "int32, one hot value")
         if n > 20_000:
+            st = handle.bucket_stats()
+            assert st["fallback"] == 0 and st["big_buckets"] == 1, st
+        many = (rng.integers(0, 600, size=n, dtype=np.int64) * 7_000_001 - (1 << 31)).astype(np.int32)  # 600 values: too many big buckets, the fallback passes undo the map
+        assert np.array_equal(sort_typed(many, capi.KEY_I32, schedule), np.sort(many)), (n, "int32, 600 values")
+        if n > 3_000_000:
             assert handle.bucket_stats()["fallback"] == 1
         nonneg = rng.integers(0, 1 << 16, size=n, dtype=np.int64).astype(np.int32)  # 16 varying bits: no local sort, plain map-back
         assert np.array_equal(sort_typed(nonneg, capi.KEY_I32, schedule), np.sort(nonneg)), (n, "int32 in [0, 65535]")

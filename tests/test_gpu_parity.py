@@ -199,6 +199,40 @@ def test_single_sort_matches_oracle(dev, oracle, built_lib):
             assert oracle.test_sort(oracle.single_sort(keys), to_host(bufs[0])) == -1, (n, mx)
 
 
+def test_small_sorts_one_launch_and_its_gated_second_kernel(handle, dev, oracle):
+    """vkrs_single_sort below 6141 keys: the keys are one item of the local sort (small_sort_kernel); only an
+    over-full bin -- a few distinct values far apart -- leaves the work to the four-pass kernel behind it."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(11)
+
+    def run(keys):
+        b0, b1 = to_dev(keys, dev), torch.zeros(keys.shape[0], dtype=torch.int32, device=dev)
+        handle.single_sort(b0, b1, capi.SinglePushConstants(keys.shape[0]))
+        handle.check_device_error()
+        return to_host(b0)
+
+    for n in (1, 2, 3, 31, 32, 33, 255, 256, 1000, 4095, 4096, 6139, 6140, 6141, 7000):
+        cases = {
+            "uniform32": oracle.generate_random(n, 70 + n, 0xFFFFFFFF),
+            "reference28": oracle.generate_random(n, 71 + n, 0x0FFFFFFF),
+            "narrow": (np.uint32(0xFFFFF000) + rng.integers(0, 4000, n, dtype=np.uint32)).astype(np.uint32),  # exact mode, up to 2^32 - 1
+            "all_equal": np.full(n, 0x80000000, dtype=np.uint32),
+            "extremes": rng.choice(np.array([0, 0xFFFFFFFF], dtype=np.uint32), n),                 # two values, the whole key range apart
+            "few_far_apart": rng.choice(np.array([5, 1 << 20, 3 << 30, 0xFFFFFFF0], dtype=np.uint32), n),  # over-full bins: the gated kernel sorts
+            "sorted": np.sort(oracle.generate_random(n, 72 + n, 0xFFFFFFFF)),
+            "descending": np.sort(oracle.generate_random(n, 73 + n, 0xFFFFFFFF))[::-1].copy(),
+        }
+        for name, keys in cases.items():
+            assert np.array_equal(run(keys), np.sort(keys)), (n, name)
+    # unaligned sub-buffer
+    base = to_dev(oracle.generate_random(3003, 5, 0xFFFFFFFF), dev)
+    view = base[3:]
+    want = np.sort(to_host(view))
+    handle.single_sort(view, torch.zeros(3000, dtype=torch.int32, device=dev), capi.SinglePushConstants(3000))
+    assert np.array_equal(to_host(view), want)
+
+
 def test_sort_auto_crossover(handle, dev, oracle):
     for n in (1, 1000, 4096, 4097, 12_288, 12_289, 100_000):
         keys = oracle.generate_random(n, 17 + n, 0xFFFFFFFF)

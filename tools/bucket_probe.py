@@ -160,7 +160,9 @@ def main():
             timing(h, "uniform32", n_big, [capi.SCHEDULE_BUCKET])
             if not os.environ.get("PROBE_ONLY_UNIFORM"):
                 timing(h, "reference28", n_big, [capi.SCHEDULE_BUCKET])
-                timing(h, "dup1024", n_big // 4, [capi.SCHEDULE_BUCKET])
+                timing(h, "hot_prefix", n_big, [capi.SCHEDULE_BUCKET])
+                timing(h, "sorted", n_big, [capi.SCHEDULE_BUCKET])
+                timing(h, "dup1024", n_big, [capi.SCHEDULE_BUCKET])
         out(kind="done", seconds=round(time.time() - t0, 1))
         return
     if correctness(h):

@@ -345,10 +345,11 @@ class Handle:
 
     def bucket_stats(self, stream=None) -> dict:
         """Control words of the last bucket-schedule sort (synchronises the stream)."""
-        out = (ctypes.c_uint32 * 8)()
+        out = (ctypes.c_uint32 * 16)()
         self._check(self._lib.vkrs_bucket_stats(self._h, out, _stream(stream)))
-        names = ("shift1", "shift2", "fallback", "recount", "key_min", "max_bucket", "pieces1", "pieces2")
-        return dict(zip(names, (int(v) for v in out)))
+        names = ("shift1", "shift2", "fallback", "recount", "key_min", "max_bucket", "pieces1", "pieces2", "key_max", "_", "base",
+                 "big_buckets", "big_items")
+        return {k: int(v) for k, v in zip(names, out) if k != "_"}
 
     def set_key_span_hint(self, lo_key: int = 0, hi_key: int = 0xFFFFFFFF):
         """All keys of the following keys-only sorts lie in [lo_key, hi_key]; defaults = no hint."""

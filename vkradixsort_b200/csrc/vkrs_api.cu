@@ -412,6 +412,10 @@ struct MsdWorkspace {
     uint32_t *bucket_start; // 257: starts of the 256 buckets of pass 1
     uint32_t *sub_start;    // 65537: starts of the (digit1, digit2) buckets
     uint32_t *hist[2];
+    BigBucket *big;         // buckets above LOCAL_MAX keys (counting path)
+    uint32_t *big_done;     // finished histogram chunks per big bucket (zero between sorts)
+    uint32_t *big_vcs;      // first positions of every BIG_VCHUNK values, per big bucket
+    uint32_t *big_pool;     // the counters of all big buckets (zero between sorts)
     size_t bytes;
     MsdWorkspace(unsigned char *base, uint32_t segments) {
         const size_t max_pieces = (size_t) segments + RADIX;
@@ -430,6 +434,10 @@ struct MsdWorkspace {
         }
         bucket_start = reinterpret_cast<uint32_t *>(take((RADIX + 1) * sizeof(uint32_t)));
         sub_start = reinterpret_cast<uint32_t *>(take(((size_t) MSD_SUBS + 1) * sizeof(uint32_t)));
+        big = reinterpret_cast<BigBucket *>(take((size_t) BIG_MAX * sizeof(BigBucket)));
+        big_done = reinterpret_cast<uint32_t *>(take((size_t) BIG_MAX * sizeof(uint32_t)));
+        big_vcs = reinterpret_cast<uint32_t *>(take((size_t) BIG_MAX * BIG_VCS_STRIDE * sizeof(uint32_t)));
+        big_pool = reinterpret_cast<uint32_t *>(take((size_t) BIG_POOL_WORDS * sizeof(uint32_t)));
         bytes = off;
     }
 };
@@ -588,16 +596,16 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
     {
         // the item window is picked on the device (lt_window): the table is sized for the smallest one
         const uint32_t item_stride = (uint32_t) (((uint64_t) n + LT_MIN_WINDOW - 1) / LT_MIN_WINDOW) + 1;
-        r = grow(h, h->msd_items, h->msd_items_cap, 2 * (uint64_t) item_stride, sizeof(uint32_t), false);
+        // (+ the list of the items msd_local_tile_kernel leaves to msd_local_redo_kernel)
+        r = grow(h, h->msd_items, h->msd_items_cap, 3 * (uint64_t) item_stride, sizeof(uint32_t), false);
         if (r) return r;
-        uint32_t *item_first = h->msd_items, *item_lo = h->msd_items + item_stride;
+        uint32_t *item_first = h->msd_items, *item_lo = h->msd_items + item_stride, *redo = h->msd_items + 2 * (size_t) item_stride;
         {
             LaunchScope scope(h, "msd_items_kernel", s);
             VKRS_CUDA(h, launch_pdl(msd_items_kernel, dim3(MSD_SUBS / 256), dim3(256), 0, s, (const uint32_t *) w.sub_start, MSD_SUBS, n,
-                                    item_first, item_lo, item_stride, (const MsdPlan *) w.plan));
+                                    item_first, item_lo, item_stride, w.plan, w.big));
         }
         uint32_t grid = (uint32_t) (h->sm_count * VKRS_LT_MIN_BLOCKS);
-        if (grid > item_stride - 1) grid = item_stride - 1;
         if (XF != 0) {
             static thread_local int configured_device = -1;
             if (configured_device != h->device) {
@@ -606,10 +614,40 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
                 configured_device = h->device;
             }
         }
-        LaunchScope scope(h, "msd_local_tile_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
-                                (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
-                                (const MsdPlan *) w.plan, h->msd_use_bins, h->debug_counters));
+        {
+            LaunchScope scope(h, "msd_local_tile_kernel", s);
+            VKRS_CUDA(h, launch_pdl(msd_local_tile_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0,
+                                    (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const uint32_t *) item_lo, n,
+                                    w.plan, h->msd_use_bins, h->debug_counters, redo));
+        }
+        {
+            static thread_local int configured_device = -1;
+            if (configured_device != h->device) {
+                r = set_smem(h, msd_local_redo_kernel<XF>, sizeof(LocalRedoSmem));
+                if (r) return r;
+                configured_device = h->device;
+            }
+            LaunchScope scope(h, "msd_local_redo_kernel", s);
+            VKRS_CUDA(h, launch_pdl(msd_local_redo_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalRedoSmem), s, buf0,
+                                    (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const MsdPlan *) w.plan, (const uint32_t *) redo));
+        }
+        // buckets too large for shared memory ("big": msd_items_kernel listed them) are sorted by counting: a histogram of
+        // their low bits, then a fill.  Both kernels exit at once when there are none.
+        {
+            constexpr size_t big_smem = (32768 + 40) * sizeof(uint32_t);
+            static thread_local int configured_device = -1;
+            if (configured_device != h->device) {
+                r = set_smem(h, msd_big_hist_kernel<XF>, big_smem);
+                if (r) return r;
+                configured_device = h->device;
+            }
+            LaunchScope scope(h, "msd_big_hist_kernel", s);
+            VKRS_CUDA(h, launch_pdl(msd_big_hist_kernel<XF>, dim3(h->sm_count), dim3(BIG_HIST_THREADS), big_smem, s, (const uint32_t *) buf0,
+                                    (const MsdPlan *) w.plan, (const BigBucket *) w.big, w.big_pool, w.big_done, w.big_vcs));
+        }
+        LaunchScope scope(h, "msd_big_fill_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_big_fill_kernel<XF>, dim3(grid), dim3(512), 0, s, buf0, (const MsdPlan *) w.plan, (const BigBucket *) w.big,
+                                w.big_pool, (const uint32_t *) w.big_vcs));
     }
     if (h->msd_stop_after == 3) return VKRS_OK;
     // ---- fallback: four stable LSD passes that only work if some bucket was too large ----
@@ -788,7 +826,7 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         uint32_t ctas, segments, seg_keys;
         int r = msd_prepare(h, n, ctas, segments, seg_keys);
         if (!r) r = grow(h, h->seg_hist, h->seg_hist_rows, (uint64_t) h->sm_count * 4, RADIX * sizeof(uint32_t), false);
-        if (!r) r = grow(h, h->msd_items, h->msd_items_cap, 2 * ((uint64_t) (n + LT_MIN_WINDOW - 1) / LT_MIN_WINDOW + 1), sizeof(uint32_t), false);
+        if (!r) r = grow(h, h->msd_items, h->msd_items_cap, 3 * ((uint64_t) (n + LT_MIN_WINDOW - 1) / LT_MIN_WINDOW + 1), sizeof(uint32_t), false);
         if (r) {
             g_create_error = h->error;
             vkrs_destroy(h);
@@ -920,15 +958,15 @@ const char *vkrs_schedule_name(int schedule) {
 
 // Control words of the last bucket-schedule sort: {shift1, shift2, fallback, recount, smallest key, max_sub,
 // pieces of pass 1, pieces of pass 2}.  Synchronises `stream`.
-int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8, void *stream) {
+int vkrs_bucket_stats(vkrs_handle h, uint32_t *out8 /* 16 words */, void *stream) {
     if (!h) return VKRS_ERR_INVALID_ARGUMENT;
     if (!out8) return fail(h, VKRS_ERR_INVALID_ARGUMENT, "out8 is NULL");
-    static_assert(sizeof(MsdPlan) == 11 * sizeof(uint32_t), "vkrs_bucket_stats copies the first 8 words of the plan");
-    memset(out8, 0, 8 * sizeof(uint32_t));
+    static_assert(sizeof(MsdPlan) == 16 * sizeof(uint32_t), "vkrs_bucket_stats copies the plan");
+    memset(out8, 0, 16 * sizeof(uint32_t));
     if (!h->msd_ws) return VKRS_OK;
     DeviceGuard guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    VKRS_CUDA(h, cudaMemcpyAsync(out8, h->msd_ws, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     VKRS_CUDA(h, cudaStreamSynchronize(s));
     return VKRS_OK;
 }
@@ -1281,9 +1319,27 @@ int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_s
         if (r) return r;
         configured_device = h->device;
     }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t *gate = nullptr;
+    if (n <= (uint32_t) LT_CAP - 4u) {
+        // one launch, a handful of barriers: the keys are one item of the local sort (small_sort_kernel).  Only an over-full
+        // bin (a few distinct values far apart) leaves the work to the four-pass kernel behind it, which otherwise exits at once.
+        static thread_local int small_configured = -1;
+        if (small_configured != h->device) {
+            int r = set_smem(h, small_sort_kernel, sizeof(LocalTileSmem));
+            if (r) return r;
+            small_configured = h->device;
+        }
+        uint32_t *redo = h->ctrl + vkrs_context::CTRL_ERROR + 1;
+        {
+            LaunchScope scope(h, "small_sort_kernel", s);
+            VKRS_CUDA(h, launch_pdl(small_sort_kernel, dim3(1), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0, n, redo));
+        }
+        gate = redo;
+    }
     {
-        LaunchScope scope(h, "single_sort_kernel", static_cast<cudaStream_t>(stream));
-        kernel<<<1, SINGLE_THREADS, sizeof(Sorter::Smem), static_cast<cudaStream_t>(stream)>>>(buf0, buf1, n);
+        LaunchScope scope(h, "single_sort_kernel", s);
+        VKRS_CUDA(h, launch_pdl(kernel, dim3(1), dim3(SINGLE_THREADS), sizeof(Sorter::Smem), s, buf0, buf1, n, gate));
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;

@@ -324,7 +324,9 @@ staged_scatter_kernel(const uint32_t *__restrict__ elements_in, uint32_t *__rest
 // =====================================================================================
 template <int THREADS, int KPT, int MATCH>
 __global__ void __launch_bounds__(THREADS, 1)
-single_sort_kernel(uint32_t *buf0, uint32_t *buf1, uint32_t n) {
+single_sort_kernel(uint32_t *buf0, uint32_t *buf1, uint32_t n, const uint32_t *__restrict__ gate /* may be NULL: the kernel only works if *gate != 0 */) {
+    grid_dependency_wait();
+    if (gate && *gate == 0) return;
     using Sorter = TileSorter<uint32_t, false, THREADS, KPT, MATCH>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typename Sorter::Smem &s = *reinterpret_cast<typename Sorter::Smem *>(smem_raw);

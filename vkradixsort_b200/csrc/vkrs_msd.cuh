@@ -55,6 +55,26 @@ struct MsdPlan {
     uint32_t key_max;       // largest key
     uint32_t skip_pass2;    // != 0: pass 1 already saw a bucket that is bound to overflow the local sort; pass 2 is not run
     uint32_t base;          // the digits are taken from key - base: the occupied key range starts at digit value 0
+    uint32_t num_big;       // (digit1, digit2) buckets above LOCAL_MAX keys: finished by counting (msd_big_*), not in shared memory
+    uint32_t big_items;     // work items (chunks of BIG_CHUNK keys) of their histograms
+    uint32_t num_redo;      // items the bins path of the local sort could not take: sorted bucket by bucket by msd_local_redo_kernel
+    uint32_t pad[2];
+};
+
+// Buckets too large for the shared-memory sort ("big" buckets: skewed keys -- half of the input under one 16-bit prefix,
+// a few clusters, heavy duplicates).  All their keys agree above the low `shift[1]` <= 16 bits, so a big bucket is
+// sorted by COUNTING: a histogram of the low bits (one global-memory counter per value, warp-aggregated atomics, any
+// number of CTAs per bucket), an exclusive scan, and a fill that writes every value as often as it was counted -- no
+// key moves.  4 B/key read + 4 B/key written, whatever the bucket's size.
+constexpr uint32_t BIG_MAX = 1024;                 // big buckets per sort (more: the stable LSD passes take over)
+constexpr uint32_t BIG_POOL_WORDS = 16u << 20;     // counters of all big buckets of one sort: 64 MB (256 buckets at 16 low bits)
+constexpr uint32_t BIG_CHUNK = 65536;              // keys per histogram work item
+constexpr uint32_t BIG_VCHUNK = 1024;              // values per fill work item
+constexpr uint32_t BIG_VCS_STRIDE = 65536 / BIG_VCHUNK + 8; // first positions of a bucket's value chunks (+ end), per bucket
+struct BigBucket {
+    uint32_t lo, hi;        // the bucket's keys: positions [lo, hi) of the array
+    uint32_t leaf;          // its (digit1, digit2) index: the keys are base + (leaf << low_bits) + [0, 2^low_bits)
+    uint32_t first_item;    // its first histogram work item
 };
 
 constexpr int MSD_PLAN_THREADS = 1024;
@@ -98,6 +118,9 @@ __global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1,
         plan->key_max = 0;
         plan->max_sub = 0;
         plan->skip_pass2 = 0;
+        plan->num_big = 0;
+        plan->big_items = 0;
+        plan->num_redo = 0;
     }
 }
 
@@ -522,15 +545,10 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                     running_base = run_start + below;
                     if (sub_start && q == qf) { // the bucket's first piece publishes the run starts
                         sub_start[b * RADIX + dgt] = run_start;
-                        // pass 1: a top-digit bucket above 256 * LOCAL_MAX keys holds a 16-bit-prefix bucket above LOCAL_MAX
-                        // (not for typed keys: their fallback passes expect the transformed keys pass 2 leaves in buf0)
-                        if (XF == 0 && pass == 0 && btotal > (uint32_t) (RADIX * LOCAL_MAX) && plan->shift[1] > 0) {
-                            plan->skip_pass2 = 1;
-                            plan->fallback = 1;
-                        }
                         if (max_sub) {
-                            if (btotal > max_sub && shift > 0) plan->fallback = 1;
-                            const uint32_t wmax = __reduce_max_sync(0xffffffffu, btotal);
+                            // the largest bucket the shared-memory sort will see (it sizes the items); a bucket above
+                            // max_sub keys with low bits left is "big": finished by counting (msd_items_kernel lists them)
+                            const uint32_t wmax = __reduce_max_sync(0xffffffffu, (btotal > max_sub && shift > 0) ? 0u : btotal);
                             if (lane == 0) atomicMax(&plan->max_sub, wmax);
                         }
                     }
@@ -593,7 +611,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 // place with 128-bit stores.
 // =====================================================================================
 #ifndef VKRS_LT_CAP
-#define VKRS_LT_CAP 6144
+#define VKRS_LT_CAP 7168
 #endif
 #ifndef VKRS_LT_BIN_BITS
 #define VKRS_LT_BIN_BITS 12
@@ -608,7 +626,12 @@ constexpr int LT_THREADS = VKRS_LT_THREADS;
 constexpr int LT_CAP = VKRS_LT_CAP; // keys per shared-memory buffer: the largest item the bins path takes
 constexpr int LT_MIN_WINDOW = 256;
 constexpr int LT_BIN_BITS = VKRS_LT_BIN_BITS;
+#ifdef VKRS_LT_BINS
+constexpr int LT_BINS = VKRS_LT_BINS; // (the bin map is a multiplication: any number of bins works)
+#else
 constexpr int LT_BINS = 1 << LT_BIN_BITS;
+#endif
+constexpr int LT_DESC = 64; // item descriptors loaded per batch (power of two, 4 * LT_DESC <= LT_THREADS)
 constexpr int LT_BIN_LIMIT = 32; // power of two (the over-full test ORs the counts)
 constexpr int LT_BPT = LT_BINS / LT_THREADS; // bins per thread in the scan: LT_BPT / 4 conflict-free 128-bit accesses
 constexpr int LT_WORK_WORDS = LT_BINS > (LT_THREADS / 32) * RADIX ? LT_BINS : (LT_THREADS / 32) * RADIX;
@@ -650,7 +673,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_t(uint32_t v, uint32_t 
 // w = 0 .. ceil(n / window); the last entry is (num_sub, n).  One thread per bucket.
 __global__ void __launch_bounds__(256)
 msd_items_kernel(const uint32_t *__restrict__ sub_start, uint32_t num_sub, uint32_t n, uint32_t *__restrict__ item_first,
-                 uint32_t *__restrict__ item_lo, uint32_t item_stride, const MsdPlan *__restrict__ plan) {
+                 uint32_t *__restrict__ item_lo, uint32_t item_stride, MsdPlan *__restrict__ plan, BigBucket *__restrict__ big) {
     grid_dependency_wait();
     if (plan->fallback != 0) return;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -659,21 +682,48 @@ msd_items_kernel(const uint32_t *__restrict__ sub_start, uint32_t num_sub, uint3
     const uint32_t num_items = (n + window - 1) / window;
     if (num_items + 1 > item_stride) return; // cannot happen: the table is sized for the smallest window
     const uint32_t s_j = __ldcg(sub_start + j);
+    // ---- a big bucket: listed for the counting path, with one work item per BIG_CHUNK keys ----
+    {
+        const uint32_t e_j = __ldcg(sub_start + j + 1), low_bits = plan->shift[1];
+        if (e_j - s_j > (uint32_t) LOCAL_MAX && low_bits > 0) {
+            const uint32_t limit = min(BIG_MAX, BIG_POOL_WORDS >> low_bits);
+            const uint32_t k = atomicAdd(&plan->num_big, 1u);
+            if (k >= limit) {
+                plan->fallback = 1; // too many of them: the stable LSD passes sort the array
+            } else {
+                const uint32_t chunks = (e_j - s_j + BIG_CHUNK - 1) / BIG_CHUNK;
+                const uint32_t first = atomicAdd(&plan->big_items, chunks);
+                big[k] = BigBucket{s_j, e_j, j, first};
+            }
+        }
+    }
+    // windows (w_prev, w_j] start inside the buckets before this one or at it: bucket j is the first whose start is
+    // behind them.  After a bucket far larger than the window that is a long range: the warp fills it together.
     const int w_j = (int) (s_j / window);
     const int w_prev = j > 0 ? (int) (__ldcg(sub_start + j - 1) / window) : -1;
     const int last = (int) num_items - 1;
-    for (int w = w_prev + 1; w <= w_j && w <= last; ++w) {
-        item_first[w] = j;
-        item_lo[w] = s_j;
-    }
-    if (j == num_sub - 1) {
-        for (int w = w_j + 1; w <= last; ++w) { // windows in which no bucket starts (the tail of a large last bucket)
-            item_first[w] = num_sub;
-            item_lo[w] = n;
+    auto fill = [&](int from, int to, uint32_t first, uint32_t lo) { // item_first / item_lo [from, to] <- (first, lo), warp-cooperative
+        const int len = to - from + 1;
+        if (len > 0 && len <= 4)
+            for (int w = from; w <= to; ++w) {
+                item_first[w] = first;
+                item_lo[w] = lo;
+            }
+        uint32_t longer = __ballot_sync(0xffffffffu, len > 4);
+        while (longer) {
+            const int src = __ffs((int) longer) - 1;
+            longer &= longer - 1;
+            const int f0 = __shfl_sync(0xffffffffu, from, src), n0 = __shfl_sync(0xffffffffu, len, src);
+            const uint32_t a = __shfl_sync(0xffffffffu, first, src), b = __shfl_sync(0xffffffffu, lo, src);
+            for (int i = (int) (threadIdx.x & 31); i < n0; i += 32) {
+                item_first[f0 + i] = a;
+                item_lo[f0 + i] = b;
+            }
         }
-        item_first[num_items] = num_sub;
-        item_lo[num_items] = n;
-    }
+    };
+    fill(w_prev + 1, w_j < last ? w_j : last, j, s_j);
+    // windows in which no bucket starts (the tail of a large last bucket), and the end marker
+    fill(j == num_sub - 1 ? w_j + 1 : 1, j == num_sub - 1 ? last + 1 : 0, num_sub, n);
 }
 
 struct LocalTileSmem {
@@ -682,10 +732,9 @@ struct LocalTileSmem {
     alignas(16) uint32_t buf[3][LT_CAP + 8];
     // work = work_m + 4.  bins path: bin counters, then running prefixes, work[-1] stays 0; bucket path: warp_cnt[16][256]
     alignas(16) uint32_t work_m[4 + LT_WORK_WORDS];
-    uint32_t small_cnt[RADIX];                         // bucket path: byte-0 counters
-    uint32_t cand_lo[LT_THREADS], cand_hi[LT_THREADS]; // bucket path: bounds of one chunk of buckets
-    uint32_t scratch[72];
+    uint32_t scratch[72];  // (40.. : per-warp minima / maxima of small_sort_kernel)
     uint32_t params[8]; // loop invariants that are only needed once per item: kept out of the registers
+    uint32_t desc[LT_DESC][4]; // descriptors of the CTA's next items
     unsigned long long timers[16]; // phase timers of thread 0 (tuning aid, vkrs_debug_counters)
     unsigned long long t_last;
 };
@@ -1056,13 +1105,180 @@ __device__ __forceinline__ void store_item(const uint32_t *buf, uint32_t *__rest
     }
 }
 
+// Exclusive scan of a bucket's 2^low_bits counters, in place (one CTA; the counters live in L2), + vchunk_start[c] =
+// first position of value c * BIG_VCHUNK, c = 0 .. ceil(V / BIG_VCHUNK) (the last entry = the bucket's size).
+template <int THREADS>
+__device__ __forceinline__ void big_scan_bucket(uint32_t *__restrict__ counters, uint32_t low_bits, uint32_t *__restrict__ vchunk_start,
+                                                uint32_t *scratch /* 33 */) {
+    const uint32_t V = 1u << low_bits, per = (V + THREADS - 1) / THREADS, tid = threadIdx.x;
+    const uint32_t v0 = tid * per, v1 = min(V, v0 + per);
+    uint32_t sum = 0;
+    for (uint32_t v = v0; v < v1; ++v) sum += __ldcg(counters + v);
+    uint32_t total = 0;
+    uint32_t run = block_exclusive_scan_t<THREADS>(sum, scratch, &total);
+    for (uint32_t v = v0; v < v1; ++v) {
+        const uint32_t c = __ldcg(counters + v);
+        counters[v] = run;
+        if ((v & (BIG_VCHUNK - 1)) == 0) vchunk_start[v / BIG_VCHUNK] = run;
+        run += c;
+    }
+    if (tid == 0) vchunk_start[(V + BIG_VCHUNK - 1) / BIG_VCHUNK] = total;
+}
+
+// Histogram of the big buckets' low bits.  Persistent, one CTA per SM; CTA c takes a contiguous range of the work items
+// (chunks of BIG_CHUNK keys; a bucket's chunks are consecutive items), counts into a shared-memory table of 65536
+// 16-bit counters and flushes it to the bucket's global counters when the bucket changes: a value that occurs several
+// times in the CTA's share costs one global atomic, not one per key (5 x fewer for one bucket holding half of 10^8
+// keys).  A 16-bit counter that reaches 2^15 is spilled at once, so none can overflow.  The CTA that delivers a
+// bucket's last chunk turns the bucket's counters into first positions (big_scan_bucket).
+constexpr int BIG_HIST_THREADS = 1024;
+template <int XF>
+__global__ void __launch_bounds__(BIG_HIST_THREADS, 1)
+msd_big_hist_kernel(const uint32_t *__restrict__ keys, const MsdPlan *__restrict__ plan, const BigBucket *__restrict__ big,
+                    uint32_t *__restrict__ pool, uint32_t *__restrict__ big_done, uint32_t *__restrict__ big_vcs) {
+    extern __shared__ __align__(16) uint32_t big_tab[]; // 32768 words = 65536 packed counters, + 40 words of scratch
+    uint32_t *scratch = big_tab + 32768;
+    grid_dependency_wait();
+    if (plan->fallback != 0) return;
+    const uint32_t big_items = plan->big_items, num_big = plan->num_big;
+    if (big_items == 0) return;
+    const uint32_t low_bits = plan->shift[1], mask = (1u << low_bits) - 1u, words = ((1u << low_bits) + 1) >> 1;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (big_items + gridDim.x - 1) / gridDim.x;
+    const uint32_t it0 = blockIdx.x * per, it1 = min(big_items, it0 + per);
+    if (it0 >= it1) return;
+    for (uint32_t i = tid; i < words; i += BIG_HIST_THREADS) big_tab[i] = 0;
+    uint32_t cur = 0xFFFFFFFFu, cur_chunks = 0; // bucket being accumulated, chunks of it in the table
+    BigBucket bk = {};
+    uint32_t *counters = nullptr;
+    __syncthreads();
+
+    // the table goes to the bucket's global counters; the last deliverer of a bucket scans them
+    auto flush = [&]() {
+        for (uint32_t i = tid; i < words; i += BIG_HIST_THREADS) {
+            const uint32_t w = big_tab[i];
+            if (w != 0) {
+                if (w & 0xffffu) atomicAdd(counters + 2 * i, w & 0xffffu);
+                if (w >> 16) atomicAdd(counters + 2 * i + 1, w >> 16);
+                big_tab[i] = 0;
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const uint32_t chunks = (bk.hi - bk.lo + BIG_CHUNK - 1) / BIG_CHUNK;
+            scratch[34] = atomicAdd(big_done + cur, cur_chunks) + cur_chunks == chunks ? 1u : 0u;
+        }
+        __syncthreads();
+        if (scratch[34] != 0) {
+            __threadfence();
+            big_scan_bucket<BIG_HIST_THREADS>(counters, low_bits, big_vcs + (size_t) cur * BIG_VCS_STRIDE, scratch);
+            if (tid == 0) big_done[cur] = 0; // for the next sort
+        }
+        __syncthreads();
+    };
+
+    for (uint32_t it = it0; it < it1; ++it) {
+        // the bucket of this work item (the buckets were listed in any order: a linear search, uniform over the CTA)
+        uint32_t k = cur, c = 0;
+        if (cur != 0xFFFFFFFFu && it - bk.first_item < (bk.hi - bk.lo + BIG_CHUNK - 1) / BIG_CHUNK) {
+            c = it - bk.first_item;
+        } else {
+            for (k = 0; k < num_big; ++k) {
+                const BigBucket cand = big[k];
+                if (it - cand.first_item < (cand.hi - cand.lo + BIG_CHUNK - 1) / BIG_CHUNK) {
+                    c = it - cand.first_item;
+                    break;
+                }
+            }
+            if (cur != 0xFFFFFFFFu) flush();
+            cur = k;
+            cur_chunks = 0;
+            bk = big[k];
+            counters = pool + ((size_t) k << low_bits);
+        }
+        ++cur_chunks;
+        const uint32_t value_base = plan->base + (bk.leaf << low_bits);
+        const uint32_t lo = bk.lo + c * BIG_CHUNK, hi = min(bk.hi, lo + BIG_CHUNK);
+        for (uint32_t p0 = lo + 4 * tid; p0 < hi; p0 += 4 * BIG_HIST_THREADS) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = p0 + u < hi ? ((__ldcs(keys + p0 + u) - value_base) & mask) : 0xFFFFFFFFu;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (v[u] != 0xFFFFFFFFu) {
+                    const uint32_t sh = (v[u] & 1u) << 4;
+                    const uint32_t old = atomicAdd(&big_tab[v[u] >> 1], 1u << sh);
+                    if (((old >> sh) & 0xffffu) == 0x7FFFu) { // this key made it 2^15: move that much to the global counter
+                        atomicSub(&big_tab[v[u] >> 1], 0x8000u << sh);
+                        atomicAdd(counters + v[u], 0x8000u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    flush();
+}
+
+// Fill: work item (bucket k, value chunk c).  A warp takes 32 consecutive values; a value counted once or twice is
+// written by its lane, longer runs by the whole warp, 128 bytes per store.  The counters are left zero for the next sort.
+template <int XF>
+__global__ void __launch_bounds__(512)
+msd_big_fill_kernel(uint32_t *__restrict__ keys, const MsdPlan *__restrict__ plan, const BigBucket *__restrict__ big,
+                    uint32_t *__restrict__ pool, const uint32_t *__restrict__ vchunk_start_all) {
+    grid_dependency_wait();
+    if (plan->fallback != 0) return;
+    const uint32_t num_big = plan->num_big;
+    if (num_big == 0) return;
+    const uint32_t low_bits = plan->shift[1], V = 1u << low_bits;
+    const uint32_t vchunks = (V + BIG_VCHUNK - 1) / BIG_VCHUNK, items = num_big * vchunks;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    for (uint32_t it = blockIdx.x; it < items; it += gridDim.x) {
+        const uint32_t k = it / vchunks, c = it - k * vchunks;
+        const BigBucket bk = big[k];
+        uint32_t *counters = pool + ((size_t) k << low_bits);
+        const uint32_t *vcs = vchunk_start_all + (size_t) k * BIG_VCS_STRIDE;
+        const uint32_t value_base = plan->base + (bk.leaf << low_bits);
+        const uint32_t vlo = c * BIG_VCHUNK, vhi = min(V, vlo + BIG_VCHUNK);
+        const uint32_t chunk_end = __ldcg(vcs + c + 1); // first position of the value behind this chunk
+        for (uint32_t vb = vlo + 32 * warp; vb < vhi; vb += 32 * warps) {
+            const uint32_t v = vb + lane;
+            const bool valid = v < vhi;
+            const uint32_t start = valid ? __ldcg(counters + v) : chunk_end;
+            uint32_t next = __shfl_down_sync(0xffffffffu, start, 1); // first position of value v + 1
+            if (valid) {
+                if (v + 1 >= vhi) next = chunk_end;
+                else if (lane == 31) next = __ldcg(counters + v + 1);
+            }
+            const uint32_t cnt = valid ? next - start : 0u;
+            const uint32_t key = KeyXform<uint32_t, XF>::inv(value_base + v);
+            if (cnt >= 1 && cnt <= 2) {
+                keys[bk.lo + start] = key;
+                if (cnt == 2) keys[bk.lo + start + 1] = key;
+            }
+            uint32_t longer = __ballot_sync(0xffffffffu, cnt > 2);
+            while (longer) {
+                const int src = __ffs((int) longer) - 1;
+                longer &= longer - 1;
+                const uint32_t s0 = __shfl_sync(0xffffffffu, start, src), n0 = __shfl_sync(0xffffffffu, cnt, src);
+                const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
+                for (uint32_t i = lane; i < n0; i += 32) keys[bk.lo + s0 + i] = kk;
+            }
+        }
+        __syncthreads(); // every start of the chunk has been read (a warp's last lane reads its neighbour's first)
+        for (uint32_t v = vlo + threadIdx.x; v < vhi; v += blockDim.x) counters[v] = 0;
+    }
+}
+
 // XF != 0 (typed keys): the keys in the array are the transformed ones; every key is written back through the inverse map.
 template <int XF>
 __global__ void __launch_bounds__(LT_THREADS, VKRS_LT_MIN_BLOCKS)
 msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start,
                       const uint32_t *__restrict__ item_first, const uint32_t *__restrict__ item_lo, uint32_t n,
-                      const MsdPlan *__restrict__ plan, uint32_t use_bins /* 0: per-bucket path only (tests) */,
-                      unsigned long long *__restrict__ timers_out) {
+                      MsdPlan *__restrict__ plan, uint32_t use_bins /* 0: per-bucket path only (tests) */,
+                      unsigned long long *__restrict__ timers_out, uint32_t *__restrict__ redo) {
     extern __shared__ __align__(128) unsigned char smem_raw_tile[];
     LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_tile);
     const int tid = threadIdx.x;
@@ -1083,10 +1299,11 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
 
     uint32_t w = blockIdx.x;
     if (w >= num_items) return;
-    // descriptors one item ahead of the keys, keys one item ahead of the sort.  (Measured alternatives, both slower:
-    // descriptors fetched further ahead into a shared-memory ring by a plain load left in flight -- every later
-    // instruction that shares its scoreboard slot waits for it, and the warp that issued it arrives late at each
-    // barrier, +75 us -- or by cp.async together with the keys, +50 us.)
+    // Keys one item ahead of the sort; the descriptors (lo, hi, first bucket, end bucket) of the CTA's next 64 items are
+    // loaded together every 64 items, right in front of a barrier, so that no item waits for a global load.
+    // (Measured alternatives, both slower than even a load per item: a shared-memory ring filled by a plain load left in
+    // flight across the item -- every later instruction that shares its scoreboard slot waits for it, and the warp that
+    // issued it arrives late at each barrier, +75 us -- or by cp.async together with the keys, +50 us.)
     uint32_t lo = __ldcg(item_lo + w), hi = __ldcg(item_lo + w + 1);
     uint32_t j0 = __ldcg(item_first + w), j1 = __ldcg(item_first + w + 1);
     uint32_t b_in = 0, b_sorted = 1, b_next = 2; // roles of the three key buffers
@@ -1099,22 +1316,20 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         sm.t_last = clock64();
     }
 #endif
-    uint32_t mslot = 0;
+    uint32_t mslot = 0, iter = 0;
     uint32_t pend_lo = 0, pend_size = 0; // the previous item, sorted, waits in buf[b_sorted] for its copy back to the array
-    for (; w < num_items; w += gridDim.x) {
-        const uint32_t wn = w + gridDim.x;
-        uint32_t nlo = 0, nhi = 0, nj0 = 0, nj1 = 0;
-        if (wn < num_items) {
-            nlo = __ldcg(item_lo + wn);
-            nhi = __ldcg(item_lo + wn + 1);
-            nj0 = __ldcg(item_first + wn);
-            nj1 = __ldcg(item_first + wn + 1);
+    for (; w < num_items; w += gridDim.x, ++iter) {
+        if ((iter & (LT_DESC - 1)) == 0 && tid < 4 * LT_DESC) { // the descriptors of the items behind this one
+            const uint32_t item = w + ((tid >> 2) + 1) * gridDim.x;
+            sm.desc[tid >> 2][tid & 3] = item < num_items ? __ldcg(((tid & 3) < 2 ? item_lo : item_first) + item + (tid & 1)) : 0u;
         }
         const uint32_t size = hi - lo;
         cp_async_wait_all();
         LT_MARK(sm, 9);
         __syncthreads(); // this item's keys are in buf[b_in]; buf[b_next] and the work area are free; buf[b_sorted] = previous item, sorted
         LT_MARK(sm, 0);
+        const uint32_t *nd = sm.desc[iter & (LT_DESC - 1)];
+        const uint32_t nlo = nd[0], nhi = nd[1], nj0 = nd[2], nj1 = nd[3];
         // ---- start the copy of the next item: it has the whole of this item's sort to land ----
         prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned);
         if (tid == 0) sm.params[2 + (mslot ^ 1)] = lt_bin_mult(nj1 > nj0 ? nj1 - nj0 : 1u, low_bits);
@@ -1138,30 +1353,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                     pend_size = size;
                 }
             }
-            if (todo) {
-                // the item's buckets one by one (empty and one-key buckets are skipped in chunks)
-                __syncthreads();
-                for (uint32_t jb = j0; jb < j1; jb += LT_THREADS) {
-                    const uint32_t j = jb + tid;
-                    uint32_t blo = 0, bhi = 0;
-                    if (j < j1) {
-                        blo = __ldcg(sub_start + j);
-                        bhi = __ldcg(sub_start + j + 1);
-                    }
-                    sm.cand_lo[tid] = blo;
-                    sm.cand_hi[tid] = bhi;
-                    if (__syncthreads_or(bhi - blo > (XF != 0 ? 0u : 1u)) == 0) continue;
-                    const uint32_t chunk = j1 - jb < (uint32_t) LT_THREADS ? j1 - jb : (uint32_t) LT_THREADS;
-                    for (uint32_t c = 0; c < chunk; ++c) {
-                        const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
-                        if (XF != 0 && chi - clo == 1 && tid == 0) keys[clo] = KeyXform<uint32_t, XF>::inv(keys[clo]);
-                        if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
-                            local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, sm.params[0] + ((jb + c) << low_bits), low_bits > 8, sm.buf[b_sorted], sm.buf[b_in], sm.work_m + 4,
-                                                          sm.small_cnt, sm.scratch);
-                    }
-                    __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
-                }
-            }
+            if (todo && tid == 0) redo[atomicAdd(&plan->num_redo, 1u)] = w; // rare: msd_local_redo_kernel sorts it bucket by bucket
         } else if (XF != 0 && size == 1 && tid == 0) {
             keys[lo] = KeyXform<uint32_t, XF>::inv(keys[lo]);
         }
@@ -1187,6 +1379,101 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     }
 #endif
     cp_async_wait_all();
+}
+
+// =====================================================================================
+// Small sorts in ONE launch and a handful of barriers: up to LT_CAP - 4 keys are one "item" of the local sort -- load,
+// smallest / largest key, the multiplicative bin map over that span, count, scan, place, fix-up, store.  (The
+// reference's single_radixsort.comp runs four digit passes with three barriers per 256 keys inside one work group;
+// the restated kernel, single_sort_kernel, takes 35 us for 1000 keys -- launch latency and ~50 barriers.)  An over-full
+// bin (a few distinct values far apart) leaves the keys untouched and raises *redo: single_sort_kernel, enqueued
+// behind this kernel and gated on that word, sorts them.
+// =====================================================================================
+__global__ void __launch_bounds__(LT_THREADS, 1)
+small_sort_kernel(uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ redo) {
+    extern __shared__ __align__(128) unsigned char smem_raw_small[];
+    LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_small);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    grid_dependency_wait();
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0;
+    for (uint32_t p = tid; p < n; p += LT_THREADS) {
+        const uint32_t k = keys[p];
+        sm.buf[0][p] = k;
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+        sm.scratch[40 + warp] = kmin;
+        sm.scratch[56 + warp] = kmax;
+    }
+    __syncthreads();
+    for (int w = 0; w < LT_THREADS / 32; ++w) {
+        kmin = min(kmin, sm.scratch[40 + w]);
+        kmax = max(kmax, sm.scratch[56 + w]);
+    }
+    const uint64_t span = (uint64_t) (kmax - kmin) + 1u;
+    const bool exact = span <= (uint64_t) LT_BINS;
+    uint32_t mult = 0xFFFFFFFFu;
+    if (!exact) mult = (uint32_t) (__fdividef((float) LT_BINS * 4294967296.0f, (float) span) * (1.0f - 1.0f / 2097152.0f));
+    const bool todo = local_tile_bins(sm, sm.buf[0], sm.buf[1], sm.buf[0], 0u, n, exact ? kmin - 1u : kmin, mult, exact);
+    if (tid == 0) *redo = todo ? 1u : 0u;
+    if (todo) return;
+    __syncthreads();
+    store_item<0>(sm.buf[0], keys, 0u, n, (reinterpret_cast<uintptr_t>(keys) & 15) == 0);
+}
+
+// =====================================================================================
+// The items the bins path could not take (an over-full bin: heavy duplicates; an item that does not fit a buffer
+// because a big bucket lies in its window; VKRS_LOCAL_BINS=0), bucket by bucket with local_bucket_sort.  A kernel of
+// its own: inlined into msd_local_tile_kernel this rarely used path cost the hot loop its registers (64 with 76 bytes
+// of spills against 52 without: 555 -> 463 us for 10^8 keys).  Exits at once when the list is empty.
+// =====================================================================================
+struct LocalRedoSmem {
+    alignas(16) uint32_t a[LOCAL_MAX + 8], b[LOCAL_MAX + 8];
+    uint32_t warp_cnt[(LT_THREADS / 32) * RADIX];
+    uint32_t small_cnt[RADIX];
+    uint32_t cand_lo[LT_THREADS], cand_hi[LT_THREADS];
+    uint32_t scratch[40];
+};
+
+template <int XF>
+__global__ void __launch_bounds__(LT_THREADS)
+msd_local_redo_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ sub_start, const uint32_t *__restrict__ item_first,
+                      const MsdPlan *__restrict__ plan, const uint32_t *__restrict__ redo) {
+    extern __shared__ __align__(128) unsigned char smem_raw_redo[];
+    LocalRedoSmem &sm = *reinterpret_cast<LocalRedoSmem *>(smem_raw_redo);
+    const uint32_t tid = threadIdx.x;
+    grid_dependency_wait();
+    if (plan->fallback != 0) return;
+    const uint32_t num_redo = plan->num_redo, low_bits = plan->shift[1], kbase = plan->base;
+    for (uint32_t r = blockIdx.x; r < num_redo; r += gridDim.x) {
+        const uint32_t w = redo[r];
+        const uint32_t j0 = __ldcg(item_first + w), j1 = __ldcg(item_first + w + 1);
+        // the item's buckets one by one (empty and one-key buckets are skipped in chunks; buckets above LOCAL_MAX
+        // keys are not touched: they are "big" and sorted by counting)
+        for (uint32_t jb = j0; jb < j1; jb += LT_THREADS) {
+            const uint32_t j = jb + tid;
+            uint32_t blo = 0, bhi = 0;
+            if (j < j1) {
+                blo = __ldcg(sub_start + j);
+                bhi = __ldcg(sub_start + j + 1);
+            }
+            sm.cand_lo[tid] = blo;
+            sm.cand_hi[tid] = bhi;
+            if (__syncthreads_or(bhi - blo > (XF != 0 ? 0u : 1u)) == 0) continue;
+            const uint32_t chunk = j1 - jb < (uint32_t) LT_THREADS ? j1 - jb : (uint32_t) LT_THREADS;
+            for (uint32_t c = 0; c < chunk; ++c) {
+                const uint32_t clo = sm.cand_lo[c], chi = sm.cand_hi[c];
+                if (XF != 0 && chi - clo == 1 && tid == 0) keys[clo] = KeyXform<uint32_t, XF>::inv(keys[clo]);
+                if (chi - clo > 1 && chi - clo <= (uint32_t) LOCAL_MAX)
+                    local_bucket_sort<LT_THREADS, XF>(keys + clo, chi - clo, kbase + ((jb + c) << low_bits), low_bits > 8, sm.a, sm.b, sm.warp_cnt,
+                                                      sm.small_cnt, sm.scratch);
+            }
+            __syncthreads(); // cand_lo / cand_hi are rewritten by the next chunk
+        }
+    }
 }
 
 } // namespace vkrs
