@@ -15,7 +15,7 @@ h = Handle(0, n)
 pc = capi.multi_push_constants(n, 32)
 b0, b1 = torch.empty_like(bits), torch.empty_like(bits)
 for name, src, kt in (("uint32", bits, capi.KEY_U32), ("int32", bits, capi.KEY_I32), ("float32", floats, capi.KEY_F32)):
-    for sched in (capi.SCHEDULE_LSD, capi.SCHEDULE_AUTO):
+    for sched in (capi.SCHEDULE_LSD, capi.SCHEDULE_AUTO, capi.SCHEDULE_BUCKET):
         h.set_schedule(sched)
         ts = []
         for i in range(reps + 3):
@@ -30,4 +30,5 @@ for name, src, kt in (("uint32", bits, capi.KEY_U32), ("int32", bits, capi.KEY_I
         else:
             x = b0 ^ -(1 << 31); ok = bool((x[1:] >= x[:-1]).all())
         ts.sort()
-        print(json.dumps({"keys": name, "n": n, "schedule": capi.schedule_name(sched), "ms_median": round(ts[len(ts) // 2], 4), "sorted": ok}), flush=True)
+        print(json.dumps({"keys": name, "n": n, "schedule": capi.schedule_name(sched), "ms_median": round(ts[len(ts) // 2], 4), "sorted": ok,
+                          "stats": h.bucket_stats() if sched == capi.SCHEDULE_BUCKET else None}), flush=True)

@@ -1320,26 +1320,21 @@ int vkrs_single_sort(vkrs_handle h, uint32_t *buf0, uint32_t *buf1, const vkrs_s
         configured_device = h->device;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const uint32_t *gate = nullptr;
     if (n <= (uint32_t) LT_CAP - 4u) {
-        // one launch, a handful of barriers: the keys are one item of the local sort (small_sort_kernel).  Only an over-full
-        // bin (a few distinct values far apart) leaves the work to the four-pass kernel behind it, which otherwise exits at once.
+        // one launch, a handful of barriers: the keys are one item of the local sort (small_sort_kernel)
         static thread_local int small_configured = -1;
         if (small_configured != h->device) {
             int r = set_smem(h, small_sort_kernel, sizeof(LocalTileSmem));
             if (r) return r;
             small_configured = h->device;
         }
-        uint32_t *redo = h->ctrl + vkrs_context::CTRL_ERROR + 1;
-        {
-            LaunchScope scope(h, "small_sort_kernel", s);
-            VKRS_CUDA(h, launch_pdl(small_sort_kernel, dim3(1), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0, n, redo));
-        }
-        gate = redo;
+        LaunchScope scope(h, "small_sort_kernel", s);
+        VKRS_CUDA(h, launch_pdl(small_sort_kernel, dim3(1), dim3(LT_THREADS), sizeof(LocalTileSmem), s, buf0, n));
+        return VKRS_OK;
     }
     {
         LaunchScope scope(h, "single_sort_kernel", s);
-        VKRS_CUDA(h, launch_pdl(kernel, dim3(1), dim3(SINGLE_THREADS), sizeof(Sorter::Smem), s, buf0, buf1, n, gate));
+        VKRS_CUDA(h, launch_pdl(kernel, dim3(1), dim3(SINGLE_THREADS), sizeof(Sorter::Smem), s, buf0, buf1, n, (const uint32_t *) nullptr));
     }
     VKRS_CUDA(h, cudaGetLastError());
     return VKRS_OK;

@@ -1386,11 +1386,11 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
 // smallest / largest key, the multiplicative bin map over that span, count, scan, place, fix-up, store.  (The
 // reference's single_radixsort.comp runs four digit passes with three barriers per 256 keys inside one work group;
 // the restated kernel, single_sort_kernel, takes 35 us for 1000 keys -- launch latency and ~50 barriers.)  An over-full
-// bin (a few distinct values far apart) leaves the keys untouched and raises *redo: single_sort_kernel, enqueued
-// behind this kernel and gated on that word, sorts them.
+// bin (a few distinct values far apart) sends the keys through a bitonic network in shared memory instead.
 // =====================================================================================
+static_assert(2 * (LT_CAP + 8) >= 8192 && LT_CAP <= 8192, "the bitonic fallback of small_sort_kernel pads to at most 8192 keys in two buffers");
 __global__ void __launch_bounds__(LT_THREADS, 1)
-small_sort_kernel(uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict__ redo) {
+small_sort_kernel(uint32_t *__restrict__ keys, uint32_t n) {
     extern __shared__ __align__(128) unsigned char smem_raw_small[];
     LocalTileSmem &sm = *reinterpret_cast<LocalTileSmem *>(smem_raw_small);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1418,8 +1418,30 @@ small_sort_kernel(uint32_t *__restrict__ keys, uint32_t n, uint32_t *__restrict_
     uint32_t mult = 0xFFFFFFFFu;
     if (!exact) mult = (uint32_t) (__fdividef((float) LT_BINS * 4294967296.0f, (float) span) * (1.0f - 1.0f / 2097152.0f));
     const bool todo = local_tile_bins(sm, sm.buf[0], sm.buf[1], sm.buf[0], 0u, n, exact ? kmin - 1u : kmin, mult, exact);
-    if (tid == 0) *redo = todo ? 1u : 0u;
-    if (todo) return;
+    if (todo) {
+        // an over-full bin (a few distinct values far apart): a bitonic network over the keys, padded with all-ones to
+        // a power of two, in the first two buffers taken as one (2 * (LT_CAP + 8) >= 8192 words).  Rare and small.
+        uint32_t *a = sm.buf[0];
+        uint32_t m = 1;
+        while (m < n) m <<= 1;
+        __syncthreads();
+        for (uint32_t p = n + tid; p < m; p += LT_THREADS) a[p] = 0xFFFFFFFFu;
+        __syncthreads();
+        for (uint32_t k = 2; k <= m; k <<= 1)
+            for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = tid; i < m; i += LT_THREADS) {
+                    const uint32_t l = i ^ j;
+                    if (l > i) {
+                        const uint32_t x = a[i], y = a[l];
+                        if (((i & k) == 0) == (x > y)) {
+                            a[i] = y;
+                            a[l] = x;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+    }
     __syncthreads();
     store_item<0>(sm.buf[0], keys, 0u, n, (reinterpret_cast<uintptr_t>(keys) & 15) == 0);
 }
