@@ -19,9 +19,27 @@ for sched in (capi.SCHEDULE_LSD_UNSTABLE_FIRST, capi.SCHEDULE_BUCKET):
             assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)), (sched, n, hex(mask))
 h.set_schedule(capi.SCHEDULE_BUCKET)
 n = 120_001
-k = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)  # fallback
+k = ((rng.integers(0, 4, n, dtype=np.uint32) << 30) | rng.integers(0, 1 << 16, n, dtype=np.uint32)).astype(np.uint32)  # 4 big buckets: counted
 b0 = dv(k); h.multi_sort(b0, torch.empty_like(b0), None, capi.multi_push_constants(n, 32)); torch.cuda.synchronize()
-assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)) and h.bucket_stats()["fallback"] == 1
+st = h.bucket_stats()
+assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)) and st["fallback"] == 0 and st["big_buckets"] == 4, st
+m = 400_000  # half of the keys under one prefix: one big bucket, items next to it go through the redo kernel
+k = np.where(rng.random(m) < 0.5, np.uint32(0x2BCD0000) | rng.integers(0, 1 << 16, m, dtype=np.uint32),
+             rng.integers(0, 1 << 32, m, dtype=np.uint64).astype(np.uint32)).astype(np.uint32)
+b0 = dv(k); h.multi_sort(b0, torch.empty_like(b0), None, capi.multi_push_constants(m, 32)); torch.cuda.synchronize()
+st = h.bucket_stats()
+assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)) and st["fallback"] == 0 and st["big_buckets"] == 1, st
+m = 1_400_000  # 300 buckets of ~4,700 keys: more than the counter pool takes -> the gated LSD passes
+k = ((rng.integers(0, 300, m, dtype=np.uint32) << 16) * np.uint32(200) + rng.integers(0, 1 << 16, m, dtype=np.uint32)).astype(np.uint32)
+b0 = dv(k); h.multi_sort(b0, torch.empty_like(b0), None, capi.multi_push_constants(m, 32)); torch.cuda.synchronize()
+st = h.bucket_stats()
+assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)) and st["fallback"] == 1, st
+for ns, mask in ((1, 0xFFFFFFFF), (100, 0xFFFFFFFF), (3000, 0xFFFF), (7000, 0xFFFFFFFF), (7164, 0), (5000, 3)):  # the one-launch small sort; its bitonic path
+    k = (rng.integers(0, 1 << 32, size=ns, dtype=np.uint32) & np.uint32(mask)).astype(np.uint32)
+    if mask == 3: k = (k * np.uint32(0x40000000)).astype(np.uint32)
+    b0 = dv(k); b1 = torch.empty_like(b0)
+    h.single_sort(b0, b1, capi.SinglePushConstants(ns)); torch.cuda.synchronize()
+    assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k)), (ns, hex(mask))
 k = ((rng.integers(0, 1 << 14, n, dtype=np.uint32) << 18) | rng.integers(0, 4, n, dtype=np.uint32)).astype(np.uint32)  # over-full bins: per-bucket path
 b0 = dv(k); h.multi_sort(b0, torch.empty_like(b0), None, capi.multi_push_constants(n, 32)); torch.cuda.synchronize()
 assert np.array_equal(b0.cpu().numpy().view(np.uint32), np.sort(k))

@@ -735,6 +735,7 @@ struct LocalTileSmem {
     uint32_t scratch[72];  // (40.. : per-warp minima / maxima of small_sort_kernel)
     uint32_t params[8]; // loop invariants that are only needed once per item: kept out of the registers
     uint32_t desc[LT_DESC][4]; // descriptors of the CTA's next items
+    alignas(8) uint64_t copy_bar; // completion of the item copy in flight (one arrival per prefetch_item call)
     unsigned long long timers[16]; // phase timers of thread 0 (tuning aid, vkrs_debug_counters)
     unsigned long long t_last;
 };
@@ -748,24 +749,38 @@ __device__ __forceinline__ void cp_async_16(uint32_t *smem_dst, const uint32_t *
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Starts the copy of keys [lo, hi) into buf so that key lo + i lands at buf[(lo & 3) + i]: whole 16-byte
-// groups where the array allows it, single keys for the rest.  n = size of the array.  Nothing is
-// copied when the item does not fit a buffer (it is then sorted bucket by bucket from global memory).
+// Starts the copy of keys [lo, hi) into buf so that key lo + i lands at buf[(lo & 3) + i]: the whole 16-byte groups
+// that lie inside the array with ONE 1-D TMA bulk copy issued by thread 0 (no LSU work at all: the cp.async version of
+// this copy was 9 % of the kernel's shared-memory wavefronts and 6 % of its instructions), single keys (cp.async) for
+// the rest -- the last keys of an array whose size is not a multiple of four, or an array that is not 16-byte aligned.
+// n = size of the array.  Nothing is copied when the item does not fit a buffer (it goes to the redo list).  Every
+// call completes one phase of `bar` (thread 0 arrives once, with the bulk copy's byte count if there is one); the
+// consumer waits for cp_async_wait_all() AND that phase.  Called by all threads, after a barrier that follows the last
+// read of buf.
 __device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__restrict__ keys, uint32_t lo, uint32_t hi, uint32_t n,
-                                              bool base_aligned) {
+                                              bool base_aligned, uint64_t *bar) {
     const uint32_t tid = threadIdx.x;
+    uint32_t bulk_bytes = 0;
+    const uint32_t a0 = lo & ~3u;
     if (hi > lo && hi - lo <= (uint32_t) LT_CAP) {
-        const uint32_t a0 = lo & ~3u;
         uint32_t a1 = a0; // [a0, a1): 16-byte groups that lie inside the array
         if (base_aligned) {
             a1 = (hi + 3u) & ~3u;
             if (a1 > (n & ~3u)) a1 = n & ~3u;
             if (a1 < a0) a1 = a0;
-            for (uint32_t g = a0 + 4 * tid; g < a1; g += 4 * LT_THREADS) cp_async_16(&buf[g - a0], keys + g);
+            bulk_bytes = (a1 - a0) * (uint32_t) sizeof(uint32_t);
         }
         for (uint32_t p = (a1 > lo ? a1 : lo) + tid; p < hi; p += LT_THREADS) cp_async_4(&buf[p - a0], keys + p);
     }
     cp_async_commit();
+    if (tid == 0) {
+        if (bulk_bytes != 0) {
+            mbar_arrive_expect_tx(bar, bulk_bytes);
+            bulk_copy_g2s(buf, keys + a0, bulk_bytes, bar);
+        } else {
+            mbar_arrive(bar);
+        }
+    }
 }
 
 // Robust shared-memory sort of one bucket gk[0, cnt_keys), cnt_keys <= LOCAL_MAX, whose keys all lie in
@@ -1293,7 +1308,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     if (tid == 0) {
         sm.params[0] = plan->base; // bucket j holds the keys base + (j << low_bits) + [0, 2^low_bits)
         sm.params[1] = use_bins;
+        mbar_init(&sm.copy_bar, 1);
+        mbar_fence_init();
     }
+    __syncthreads();
     const uint32_t window = lt_window(plan->max_sub);
     const uint32_t num_items = (n + window - 1) / window;
 
@@ -1308,7 +1326,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     uint32_t j0 = __ldcg(item_first + w), j1 = __ldcg(item_first + w + 1);
     uint32_t b_in = 0, b_sorted = 1, b_next = 2; // roles of the three key buffers
     const bool base_aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
-    prefetch_item(sm.buf[b_in], keys, lo, hi, n, base_aligned);
+    prefetch_item(sm.buf[b_in], keys, lo, hi, n, base_aligned, &sm.copy_bar);
     if (tid == 0) sm.params[2] = lt_bin_mult(j1 > j0 ? j1 - j0 : 1u, low_bits); // the bin map of an item is computed one item ahead
 #ifdef VKRS_LT_TIMERS
     if (tid == 0) {
@@ -1325,13 +1343,14 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         }
         const uint32_t size = hi - lo;
         cp_async_wait_all();
+        mbar_wait(&sm.copy_bar, iter & 1u);
         LT_MARK(sm, 9);
         __syncthreads(); // this item's keys are in buf[b_in]; buf[b_next] and the work area are free; buf[b_sorted] = previous item, sorted
         LT_MARK(sm, 0);
         const uint32_t *nd = sm.desc[iter & (LT_DESC - 1)];
         const uint32_t nlo = nd[0], nhi = nd[1], nj0 = nd[2], nj1 = nd[3];
         // ---- start the copy of the next item: it has the whole of this item's sort to land ----
-        prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned);
+        prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned, &sm.copy_bar);
         if (tid == 0) sm.params[2 + (mslot ^ 1)] = lt_bin_mult(nj1 > nj0 ? nj1 - nj0 : 1u, low_bits);
         // ---- the previous item goes back to the array while this one is counted (buf[b_sorted] is first written two barriers on) ----
         if (pend_size != 0) store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
