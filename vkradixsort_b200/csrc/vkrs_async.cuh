@@ -90,6 +90,18 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
                  : "memory");
 }
 
+// 1-D TMA bulk copy shared -> global (bulk async-group completion).  The shared-memory source must have been written
+// before a fence_proxy_async() of the writing threads and a barrier; the issuing thread commits the group and, before
+// the source is overwritten, waits for the group's reads (bulk_store_wait_read) -- before the kernel ends, for the
+// group itself (bulk_store_wait_all).
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_copy_s2g(void *gmem_dst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Named barrier over a subset of the CTA's warps (id 1..15; 0 is __syncthreads).
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");

@@ -775,6 +775,7 @@ __device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__r
     cp_async_commit();
     if (tid == 0) {
         if (bulk_bytes != 0) {
+            bulk_store_wait_read(); // buf may have been the source of an earlier bulk store
             mbar_arrive_expect_tx(bar, bulk_bytes);
             bulk_copy_g2s(buf, keys + a0, bulk_bytes, bar);
         } else {
@@ -1045,6 +1046,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
             cv[k * LT_THREADS + tid] = o;
         }
         // equal bins are equal keys in exact mode: nothing to fix up, any bin size is fine
+        if (tid == 0) bulk_store_wait_read(); // gbuf may be the source of the previous item's bulk store: read before place writes it
         if (__syncthreads_or(!exact && orc >= (uint32_t) LT_BIN_LIMIT)) return true;
     }
     LT_MARK(sm, 5);
@@ -1064,6 +1066,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     if (exact) {
 #pragma unroll 4
         for (uint32_t p = tid; p < size; p += LT_THREADS) obuf[off + p] = grouped[p];
+        fence_proxy_async(); // the sorted item may leave through a bulk copy (store_item_bulk) after the next barrier
         return false;
     }
 
@@ -1086,6 +1089,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
         }
         obuf[off + r] = k;
     }
+    fence_proxy_async(); // the sorted item may leave through a bulk copy (store_item_bulk) after the next barrier
     LT_MARK(sm, 8);
     return false;
 }
@@ -1117,6 +1121,32 @@ __device__ __forceinline__ void store_item(const uint32_t *buf, uint32_t *__rest
     } else {
 #pragma unroll 4
         for (uint32_t p = tid; p < size; p += LT_THREADS) keys[lo + p] = KeyXform<uint32_t, XF>::inv(buf[off + p]);
+    }
+}
+
+// The same copy for untransformed keys in a 16-byte aligned array: the whole 16-byte groups of the item leave with ONE
+// 1-D TMA bulk copy issued by thread 0 (no LDS / STG by the CTA), the up to three keys in front of and behind them with
+// plain stores.  The writers of buf have executed fence_proxy_async() before the barrier in front of this call; thread 0
+// waits for the copy's reads before buf is written again (local_tile_bins, prefetch_item) and for the copy itself at
+// the end of the kernel.
+__device__ __forceinline__ void store_item_bulk(const uint32_t *buf, uint32_t *__restrict__ keys, uint32_t lo, uint32_t size) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t a0 = lo & ~3u, hi = lo + size;
+    const uint32_t g_lo = (lo + 3u) & ~3u, g_hi = hi & ~3u;
+    if (g_hi > g_lo) {
+        if (tid == 0) {
+            bulk_copy_s2g(keys + g_lo, buf + (g_lo - a0), (g_hi - g_lo) * (uint32_t) sizeof(uint32_t));
+            bulk_store_commit();
+        }
+        if (tid >= 32 && tid < 35) { // (a warp that does not issue the copy)
+            const uint32_t p = lo + (tid - 32);
+            if (p < g_lo) keys[p] = buf[p - a0];
+        } else if (tid >= 36 && tid < 39) {
+            const uint32_t p = g_hi + (tid - 36);
+            if (p < hi) keys[p] = buf[p - a0];
+        }
+    } else {
+        for (uint32_t p = lo + tid; p < hi; p += LT_THREADS) keys[p] = buf[p - a0];
     }
 }
 
@@ -1353,7 +1383,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         prefetch_item(sm.buf[b_next], keys, nlo, nhi, n, base_aligned, &sm.copy_bar);
         if (tid == 0) sm.params[2 + (mslot ^ 1)] = lt_bin_mult(nj1 > nj0 ? nj1 - nj0 : 1u, low_bits);
         // ---- the previous item goes back to the array while this one is counted (buf[b_sorted] is first written two barriers on) ----
-        if (pend_size != 0) store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+        if (pend_size != 0) {
+            if (XF == 0 && base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
+            else store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+        }
         pend_size = 0;
         LT_MARK(sm, 1);
         if (size > 1) {
@@ -1389,8 +1422,10 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     }
     if (pend_size != 0) {
         __syncthreads();
-        store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+        if (XF == 0 && base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
+        else store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
     }
+    if (tid == 0) bulk_store_wait_all();
 #ifdef VKRS_LT_TIMERS
     if (tid == 0 && timers_out) {
         sm.timers[10] += 1; // CTAs
