@@ -20,7 +20,7 @@ import numpy as np
 
 RADIX = 256
 LOCAL_MAX = 4096          # largest (digit1, digit2) bucket the local sort takes (vkrs_msd.cuh: LOCAL_MAX)
-LT_CAP = 7168             # keys per shared-memory buffer of the local sort (LT_CAP)
+LT_CAP = 7680             # keys per shared-memory buffer of the local sort (LT_CAP)
 LT_MIN_WINDOW = 256
 LT_BIN_BITS = 12
 LT_BINS = 1 << LT_BIN_BITS

@@ -92,9 +92,9 @@ def test_big_bucket_and_fallback_rules(oracle):
 
 
 def test_item_windows_and_bin_map():
-    assert M.lt_window(0) == 7164 & ~511 == 6656 and M.lt_window(1716) == 5120 and M.lt_window(2044) == 5120
-    assert M.lt_window(2045) == 4608 and M.lt_window(4096) == 2560 and M.lt_window(5000) == 2048
-    assert M.lt_window(7000) == 256  # cannot fit: such items go to the per-bucket path
+    assert M.lt_window(0) == 7676 & ~511 == 7168 and M.lt_window(1716) == 5632 and M.lt_window(2044) == 5632
+    assert M.lt_window(2045) == 5120 and M.lt_window(4096) == 3072 and M.lt_window(5000) == 2560
+    assert M.lt_window(7000) == 512 and M.lt_window(7500) == 256  # the last cannot fit: such items go to the per-bucket path
     assert M.hint_window(0, 0xFFFFFFFF) == (0, 24) and M.hint_window(0xC0000000, 0xFFFFFFFF) == (0xC0000000, 22)
     assert M.hint_window(0x60000000, 0x9FFFFFFF) == (0x60000000, 22)  # the span decides, not the differing bits
     # the multiplicative bin map uses all bins whatever the span, stays below LT_BINS and is monotone

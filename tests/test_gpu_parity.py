@@ -212,7 +212,7 @@ def test_small_sorts_one_launch_and_its_gated_second_kernel(handle, dev, oracle)
         handle.check_device_error()
         return to_host(b0)
 
-    for n in (1, 2, 3, 31, 32, 33, 255, 256, 1000, 4095, 4096, 6139, 6140, 6141, 7000):
+    for n in (1, 2, 3, 31, 32, 33, 255, 256, 1000, 4095, 4096, 6141, 7000, 7675, 7676, 7677, 8000):  # 7676 = the largest one-launch sort
         cases = {
             "uniform32": oracle.generate_random(n, 70 + n, 0xFFFFFFFF),
             "reference28": oracle.generate_random(n, 71 + n, 0x0FFFFFFF),

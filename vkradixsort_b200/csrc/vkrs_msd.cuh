@@ -611,7 +611,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 // place with 128-bit stores.
 // =====================================================================================
 #ifndef VKRS_LT_CAP
-#define VKRS_LT_CAP 7168
+#define VKRS_LT_CAP 7680
 #endif
 #ifndef VKRS_LT_BIN_BITS
 #define VKRS_LT_BIN_BITS 12
@@ -968,12 +968,10 @@ __device__ __forceinline__ uint32_t lt_bin_mult(uint32_t num_buckets, uint32_t l
 #else
 #define LT_MARK(sm, i) do { } while (0)
 #endif
-// Where position p of a sorted item is kept in shared memory: the low two bits are flipped by bits 5-6, so that the
-// fix-up's stores (lane l owns positions 4l .. 4l+3: a stride of four words) and the copy-out's loads (lane l reads
-// position base + l) both touch 32 different banks.
 // Bins path of one item: keys in `in[0, size)`, size <= LT_CAP - 4, umulhi(key - base, mult) < LT_BINS for every key;
-// `gbuf` is a 16-byte aligned scratch buffer.  Leaves the key of final position p in obuf[off + p] (obuf + off may be,
-// and is, `in`) and returns false, or returns true (`in` untouched) when some bin is over-full.
+// `gbuf` is a 16-byte aligned scratch buffer.  Leaves the key of final position p -- mapped back through the inverse of
+// the typed-key transform XF -- in obuf[off + p] (obuf + off may be, and is, `in`) and returns false, or returns true
+// (`in` untouched) when some bin is over-full.
 //   count   one shared-memory atomic per key
 //   scan    the bins' first positions
 //   place   a second atomic on the bin's running position: the keys, grouped by bin, in gbuf[4 .. 4 + size)
@@ -981,6 +979,7 @@ __device__ __forceinline__ uint32_t lt_bin_mult(uint32_t num_buckets, uint32_t l
 //           keys from the bin's start are compared without a branch: a key read past the bin's end belongs to a
 //           later bin and is larger (the map is monotone), so it never counts.  Larger bins (rare: the expected
 //           bin holds about one key) finish in a loop.
+template <int XF = 0>
 __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_t *in, uint32_t *gbuf, uint32_t *obuf, uint32_t off,
                                                 uint32_t size, uint32_t base, uint32_t mult, bool exact) {
     const int tid = threadIdx.x;
@@ -1065,7 +1064,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     LT_MARK(sm, 7);
     if (exact) {
 #pragma unroll 4
-        for (uint32_t p = tid; p < size; p += LT_THREADS) obuf[off + p] = grouped[p];
+        for (uint32_t p = tid; p < size; p += LT_THREADS) obuf[off + p] = KeyXform<uint32_t, XF>::inv(grouped[p]);
         fence_proxy_async(); // the sorted item may leave through a bulk copy (store_item_bulk) after the next barrier
         return false;
     }
@@ -1087,7 +1086,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
 #pragma unroll 1
             for (uint32_t j = 4; j < n; ++j) r += ((((uint64_t) g[j] << 32) | j) < me) ? 1u : 0u;
         }
-        obuf[off + r] = k;
+        obuf[off + r] = KeyXform<uint32_t, XF>::inv(k);
     }
     fence_proxy_async(); // the sorted item may leave through a bulk copy (store_item_bulk) after the next barrier
     LT_MARK(sm, 8);
@@ -1384,8 +1383,8 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
         if (tid == 0) sm.params[2 + (mslot ^ 1)] = lt_bin_mult(nj1 > nj0 ? nj1 - nj0 : 1u, low_bits);
         // ---- the previous item goes back to the array while this one is counted (buf[b_sorted] is first written two barriers on) ----
         if (pend_size != 0) {
-            if (XF == 0 && base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
-            else store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+            if (base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
+            else store_item<0>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
         }
         pend_size = 0;
         LT_MARK(sm, 1);
@@ -1398,7 +1397,7 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
                 if (sm.params[1] != 0 && size <= (uint32_t) LT_CAP - 4u) {
                     const uint32_t mult = sm.params[2 + mslot];
                     const bool exact = mult == 0;
-                    todo = local_tile_bins(sm, in, sm.buf[b_sorted], sm.buf[b_in], lo & 3u, size, exact ? base - 1u : base, exact ? 0xFFFFFFFFu : mult, exact);
+                    todo = local_tile_bins<XF>(sm, in, sm.buf[b_sorted], sm.buf[b_in], lo & 3u, size, exact ? base - 1u : base, exact ? 0xFFFFFFFFu : mult, exact);
                 }
                 if (!todo) {
                     pend_lo = lo;
@@ -1422,8 +1421,8 @@ msd_local_tile_kernel(uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     }
     if (pend_size != 0) {
         __syncthreads();
-        if (XF == 0 && base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
-        else store_item<XF>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
+        if (base_aligned) store_item_bulk(sm.buf[b_sorted], keys, pend_lo, pend_size);
+        else store_item<0>(sm.buf[b_sorted], keys, pend_lo, pend_size, base_aligned);
     }
     if (tid == 0) bulk_store_wait_all();
 #ifdef VKRS_LT_TIMERS
