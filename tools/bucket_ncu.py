@@ -1,6 +1,6 @@
 """Workload for ncu captures of one keys-only schedule: a few whole sorts of n uniform keys.
     ncu --set full --clock-control none --import-source on -k regex:'msd_(scatter|local)' -s 3 -c 3 -o gpurun_out/x \
-        python tools/bucket_ncu.py [n] [schedule] [sorts]
+        python tools/bucket_ncu.py [n] [schedule] [sorts] [hot_prefix]
 """
 import os, sys
 import torch
@@ -12,6 +12,9 @@ sorts = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev); g.manual_seed(5)
 keys = torch.randint(-(1 << 31), (1 << 31) - 1, (n,), dtype=torch.int32, device=dev, generator=g)
+if len(sys.argv) > 4 and sys.argv[4] == "hot_prefix":  # half of the keys under one 16-bit prefix (big-bucket kernels)
+    hot = torch.rand(n, device=dev, generator=g) < 0.5
+    keys = torch.where(hot, (keys & 0xFFFF) | 0x2BCD0000, keys)
 b0, b1 = torch.empty_like(keys), torch.empty_like(keys)
 h = Handle(0, n)
 h.set_schedule(sched)
