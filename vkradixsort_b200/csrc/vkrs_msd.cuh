@@ -763,19 +763,22 @@ __device__ __forceinline__ void prefetch_item(uint32_t *buf, const uint32_t *__r
     uint32_t bulk_bytes = 0;
     const uint32_t a0 = lo & ~3u;
     if (hi > lo && hi - lo <= (uint32_t) LT_CAP) {
-        uint32_t a1 = a0; // [a0, a1): 16-byte groups that lie inside the array
         if (base_aligned) {
-            a1 = (hi + 3u) & ~3u;
+            uint32_t a1 = (hi + 3u) & ~3u; // [a0, a1): 16-byte groups that lie inside the array
             if (a1 > (n & ~3u)) a1 = n & ~3u;
             if (a1 < a0) a1 = a0;
             bulk_bytes = (a1 - a0) * (uint32_t) sizeof(uint32_t);
+            if (tid == 0) {
+                bulk_store_wait_read(); // buf may have been the source of an earlier bulk store (store_item_bulk)
+                for (uint32_t p = a1 > lo ? a1 : lo; p < hi; ++p) cp_async_4(&buf[p - a0], keys + p); // at most 3: the array's last keys
+            }
+        } else {
+            for (uint32_t p = lo + tid; p < hi; p += LT_THREADS) cp_async_4(&buf[p - a0], keys + p);
         }
-        for (uint32_t p = (a1 > lo ? a1 : lo) + tid; p < hi; p += LT_THREADS) cp_async_4(&buf[p - a0], keys + p);
     }
     cp_async_commit();
     if (tid == 0) {
         if (bulk_bytes != 0) {
-            bulk_store_wait_read(); // buf may have been the source of an earlier bulk store
             mbar_arrive_expect_tx(bar, bulk_bytes);
             bulk_copy_g2s(buf, keys + a0, bulk_bytes, bar);
         } else {
