@@ -438,12 +438,21 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
     uint32_t running_base = 0; // digit thread: where the next tile's run of its digit starts
 
     auto write_out = [&](uint32_t pslot, uint32_t count) {
+        if (count == TILE) { // the usual case, without a bounds check (= a branch) per key
 #pragma unroll
-        for (int k = 0; k < KPT; ++k) {
-            const uint32_t p = gtid + k * WORKERS;
-            if (p < count) {
+            for (int k = 0; k < KPT; ++k) {
+                const uint32_t p = gtid + k * WORKERS;
                 const uint32_t key = s.sorted[p];
                 keys_out[s.bin_dst[pslot][msd_digit(key, kbase, shift)] + p] = key;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KPT; ++k) {
+                const uint32_t p = gtid + k * WORKERS;
+                if (p < count) {
+                    const uint32_t key = s.sorted[p];
+                    keys_out[s.bin_dst[pslot][msd_digit(key, kbase, shift)] + p] = key;
+                }
             }
         }
     };
@@ -472,10 +481,18 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             // ---- rank: one shared-memory atomic per key ----
             uint32_t rk[KPT];
             if (full) {
+                // The uniform-round test costs six instructions per key; it is only compiled into the loop a warp takes
+                // when the FIRST round of its chunk is uniform (one vote per tile).  A chunk that starts mixed and goes
+                // on uniform is ranked with plain atomics: slower, not wrong.
+                bool try_uniform = false;
+                if (UNIFORM_FAST) {
+                    const uint32_t d0 = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0]), kbase, shift);
+                    try_uniform = __all_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
+                }
+                if (UNIFORM_FAST && try_uniform) {
 #pragma unroll
-                for (int i = 0; i < KPT; ++i) {
-                    const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift);
-                    if (UNIFORM_FAST) {
+                    for (int i = 0; i < KPT; ++i) {
+                        const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift);
                         const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
                         if (__all_sync(0xffffffffu, d == d_first)) {
                             uint32_t b = 0;
@@ -484,9 +501,11 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                         } else {
                             rk[i] = atomicAdd(&cnt[d], 1u);
                         }
-                    } else {
-                        rk[i] = atomicAdd(&cnt[d], 1u);
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KPT; ++i)
+                        rk[i] = atomicAdd(&cnt[msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift)], 1u);
                 }
             } else {
 #pragma unroll
