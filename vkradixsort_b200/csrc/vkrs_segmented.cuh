@@ -312,22 +312,27 @@ segmented_scatter_kernel(const KeyT *__restrict__ keys_in, KeyT *__restrict__ ke
         tp = tn;                                     \
     }
 
+    auto write_one = [&](uint32_t pslot, uint32_t p) {
+        const KeyT k = s.sorted[p];
+        const uint32_t d = digit(k);
+        const uint32_t g = s.bin_dst[pslot][d] + p;
+        if (P2P) {
+            reinterpret_cast<KeyT *>(s.dst_ptr[0][d])[g] = KeyXform<KeyT, XF_OUT>::inv(k);
+            if (HAS_VALUES) reinterpret_cast<uint32_t *>(s.dst_ptr[1][d])[g] = s.sorted_v[p];
+        } else {
+            keys_out[g] = KeyXform<KeyT, XF_OUT>::inv(k);
+            if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
+        }
+    };
     auto write_out = [&](uint32_t pslot, uint32_t valid) {
-        const bool full = valid == TILE;
+        if (valid == TILE) { // the usual case, without a bounds check (= a branch) per key
 #pragma unroll
-        for (int jj = 0; jj < KPT; ++jj) {
-            const uint32_t p = gtid + jj * WORKERS;
-            const KeyT k = s.sorted[p];
-            const uint32_t d = digit(k);
-            const uint32_t g = s.bin_dst[pslot][d] + p;
-            if (full || p < valid) {
-                if (P2P) {
-                    reinterpret_cast<KeyT *>(s.dst_ptr[0][d])[g] = KeyXform<KeyT, XF_OUT>::inv(k);
-                    if (HAS_VALUES) reinterpret_cast<uint32_t *>(s.dst_ptr[1][d])[g] = s.sorted_v[p];
-                } else {
-                    keys_out[g] = KeyXform<KeyT, XF_OUT>::inv(k);
-                    if (HAS_VALUES) vals_out[g] = s.sorted_v[p];
-                }
+            for (int jj = 0; jj < KPT; ++jj) write_one(pslot, gtid + jj * WORKERS);
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < KPT; ++jj) {
+                const uint32_t p = gtid + jj * WORKERS;
+                if (p < valid) write_one(pslot, p);
             }
         }
     };
