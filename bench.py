@@ -451,6 +451,7 @@ def run_b200(args) -> int:
         total_ms = float(t.item())
     ms_per_step = total_ms / steps
     handle.check_device_error()
+    main_bucket_stats = handle.bucket_stats() if not pairs else None  # control words of the last timed sort (later configs overwrite them)
 
     # ---- verification of the last timed output (size-independent properties, on the device) ----
     # sortedness per rank + boundary order between ranks + the multiset: count, sum, XOR and the 256 top-byte bucket
@@ -646,7 +647,7 @@ def run_b200(args) -> int:
             "clocks": clocks, "gpu_launches": int(launches), "verified": bool(verified),
         }
         if not pairs:
-            line["config"]["bucket_schedule"] = handle.bucket_stats()  # shifts, fallback flag, largest bucket of the last bucket-schedule sort
+            line["config"]["bucket_schedule"] = main_bucket_stats  # shifts, fallback flag, largest bucket, big buckets of the last timed sort
         if roofline:
             line["roofline"] = roofline
         if e2e:
