@@ -615,8 +615,8 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 // bucket pass 2 saw, so that an item fits the LT_CAP keys of a shared-memory buffer (lt_window()).  An
 // item is sorted by the full key, which is the same thing because its buckets already are in order.
 //
-// msd_local_tile_kernel, one CTA per item at a time; the item's keys were copied into shared memory
-// with cp.async while the previous item was being sorted, and the sorted item goes back to the array while
+// msd_local_tile_kernel, one CTA per item at a time; the item's keys arrived in shared memory by one 1-D TMA bulk
+// copy while the previous item was being sorted, and the sorted item goes back to the array by one bulk store while
 // the next one is being counted (three key buffers rotate through the roles "this item's keys, then its
 // sorted keys", "keys grouped by bin / the previous item on its way out", "copy target").  Two ways to sort an item:
 //   bins     an order-preserving map of the item's key span onto LT_BINS bins, umulhi(key - base, mult) -- a
@@ -627,7 +627,7 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 //            unstable with atomics, byte 1 stable with the warp-private ballot ranking of the digit pass
 //            (vkrs_tile.cuh / multi_radixsort.comp:97-122).  Always correct, several times slower.
 // Nothing is written to global memory before a path has succeeded; the sorted item then goes back in
-// place with 128-bit stores.
+// place (store_item_bulk; store_item when the array is not 16-byte aligned).
 // =====================================================================================
 #ifndef VKRS_LT_CAP
 #define VKRS_LT_CAP 7680
@@ -747,7 +747,7 @@ msd_items_kernel(const uint32_t *__restrict__ sub_start, uint32_t num_sub, uint3
 
 struct LocalTileSmem {
     // three key buffers that rotate through the roles "this item's keys", "keys in sorted order" and
-    // "cp.async destination of the next item's keys" (+ slack: 16-byte copy groups, neighbour reads)
+    // "destination of the copy of the next item's keys" (+ slack: 16-byte copy groups, neighbour reads)
     alignas(16) uint32_t buf[3][LT_CAP + 8];
     // work = work_m + 4.  bins path: bin counters, then running prefixes, work[-1] stays 0; bucket path: warp_cnt[16][256]
     alignas(16) uint32_t work_m[4 + LT_WORK_WORDS];
