@@ -481,26 +481,34 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
             // ---- rank: one shared-memory atomic per key ----
             uint32_t rk[KPT];
             if (full) {
-                // The uniform-round test costs six instructions per key; it is only compiled into the loop a warp takes
-                // when the FIRST round of its chunk is uniform (one vote per tile).  A chunk that starts mixed and goes
-                // on uniform is ranked with plain atomics: slower, not wrong.
-                bool try_uniform = false;
+                // Skewed digits (sorted or constant input, half of the keys under one prefix): 32 atomics on one counter
+                // are serialised.  The warp looks at the FIRST round of its chunk (once per tile): if at least a quarter
+                // of its keys share one digit, the chunk is ranked by a loop that handles the lanes holding that "hot"
+                // digit with ONE atomic per round (a ballot, the lowest such lane adds their number, the others take
+                // their place from the ballot) and the rest with plain atomics.  That loop costs a vote and a shuffle
+                // per key, which is why it is not the only one: compiled into the common loop the test cost 10 us per
+                // pass.  A chunk that starts mixed and goes on skewed is ranked with plain atomics: slower, not wrong.
+                uint32_t d_hot = RADIX; // no hot digit
                 if (UNIFORM_FAST) {
                     const uint32_t d0 = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0]), kbase, shift);
-                    try_uniform = __all_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0));
+                    const uint32_t same = __match_any_sync(0xffffffffu, d0);
+                    const uint32_t most = __reduce_max_sync(0xffffffffu, (uint32_t) __popc(same));
+                    if (most >= 8u) {
+                        const uint32_t holders = __ballot_sync(0xffffffffu, (uint32_t) __popc(same) == most);
+                        d_hot = __shfl_sync(0xffffffffu, d0, __ffs((int) holders) - 1);
+                    }
                 }
-                if (UNIFORM_FAST && try_uniform) {
+                if (UNIFORM_FAST && d_hot != (uint32_t) RADIX) {
+                    const uint32_t lt_mask = lanemask_lt();
 #pragma unroll
                     for (int i = 0; i < KPT; ++i) {
                         const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift);
-                        const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
-                        if (__all_sync(0xffffffffu, d == d_first)) {
-                            uint32_t b = 0;
-                            if (lane == 0) b = atomicAdd(&cnt[d], 32u);
-                            rk[i] = __shfl_sync(0xffffffffu, b, 0) + lane;
-                        } else {
-                            rk[i] = atomicAdd(&cnt[d], 1u);
-                        }
+                        const uint32_t hot = __ballot_sync(0xffffffffu, d == d_hot);
+                        const int leader = __ffs((int) hot) - 1; // -1: no lane holds the hot digit in this round
+                        uint32_t b = 0;
+                        if ((int) lane == leader) b = atomicAdd(&cnt[d_hot], (uint32_t) __popc(hot));
+                        b = __shfl_sync(0xffffffffu, b, leader < 0 ? 0 : leader);
+                        rk[i] = d == d_hot ? b + (uint32_t) __popc(hot & lt_mask) : atomicAdd(&cnt[d], 1u);
                     }
                 } else {
 #pragma unroll
