@@ -321,8 +321,10 @@ msd_piece_histogram_kernel(const uint32_t *__restrict__ keys, const uint4 *__res
 //   place      key -> sorted[excl[digit] + r] in shared memory
 //   write-out  in tile order: a warp stores 128 B of consecutive positions; the write-out of tile j-1
 //              overlaps the digit threads' work on tile j.
-// UNIFORM_FAST: a round whose 32 keys share one digit (sorted or constant input) is ranked with one
-// atomic by lane 0 instead of 32 serialised ones.
+// UNIFORM_FAST: skew-aware ranking.  Per tile a warp looks at the first round of its chunk and picks one of three
+// loops: plain atomics (the usual case; none of the tests below is compiled into it), "all one digit" (sorted or
+// constant input: a uniform round is ranked with one atomic by lane 0 instead of 32 serialised ones), "hot digit"
+// (a quarter or more of the round on one digit: those lanes share one atomic per round through a ballot).
 // =====================================================================================
 template <int WORKERS, int KPT>
 struct MsdGroupSmem {
@@ -489,16 +491,31 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
                 // per key, which is why it is not the only one: compiled into the common loop the test cost 10 us per
                 // pass.  A chunk that starts mixed and goes on skewed is ranked with plain atomics: slower, not wrong.
                 uint32_t d_hot = RADIX; // no hot digit
+                bool all_one = false;   // the whole first round shares one digit (sorted or constant input): a leaner loop
                 if (UNIFORM_FAST) {
                     const uint32_t d0 = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0]), kbase, shift);
                     const uint32_t same = __match_any_sync(0xffffffffu, d0);
                     const uint32_t most = __reduce_max_sync(0xffffffffu, (uint32_t) __popc(same));
+                    all_one = most == 32u;
                     if (most >= 8u) {
                         const uint32_t holders = __ballot_sync(0xffffffffu, (uint32_t) __popc(same) == most);
                         d_hot = __shfl_sync(0xffffffffu, d0, __ffs((int) holders) - 1);
                     }
                 }
-                if (UNIFORM_FAST && d_hot != (uint32_t) RADIX) {
+                if (UNIFORM_FAST && all_one) {
+#pragma unroll
+                    for (int i = 0; i < KPT; ++i) {
+                        const uint32_t d = msd_digit(KeyXform<uint32_t, XF>::fwd(tin[chunk0 + i * 32]), kbase, shift);
+                        const uint32_t d_first = __shfl_sync(0xffffffffu, d, 0);
+                        if (__all_sync(0xffffffffu, d == d_first)) { // one atomic by lane 0 instead of 32 serialised ones
+                            uint32_t b = 0;
+                            if (lane == 0) b = atomicAdd(&cnt[d], 32u);
+                            rk[i] = __shfl_sync(0xffffffffu, b, 0) + lane;
+                        } else {
+                            rk[i] = atomicAdd(&cnt[d], 1u);
+                        }
+                    }
+                } else if (UNIFORM_FAST && d_hot != (uint32_t) RADIX) {
                     const uint32_t lt_mask = lanemask_lt();
 #pragma unroll
                     for (int i = 0; i < KPT; ++i) {
