@@ -657,6 +657,12 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 #ifndef VKRS_LT_CAP
 #define VKRS_LT_CAP 7680
 #endif
+#ifndef VKRS_LT_CP_UNROLL
+#define VKRS_LT_CP_UNROLL 16
+#endif
+#ifndef VKRS_LT_FIX_UNROLL
+#define VKRS_LT_FIX_UNROLL 8
+#endif
 #ifndef VKRS_LT_BIN_BITS
 #define VKRS_LT_BIN_BITS 12
 #endif
@@ -669,6 +675,8 @@ msd_scatter_kernel(const uint32_t *__restrict__ keys_in, uint32_t *__restrict__ 
 constexpr int LT_THREADS = VKRS_LT_THREADS;
 constexpr int LT_CAP = VKRS_LT_CAP; // keys per shared-memory buffer: the largest item the bins path takes
 constexpr int LT_MIN_WINDOW = 256;
+constexpr int LT_FIX_UNROLL = VKRS_LT_FIX_UNROLL; // positions per iteration of the fix-up loop
+constexpr int LT_CP_UNROLL = VKRS_LT_CP_UNROLL;   // keys per iteration of the count and place loops
 constexpr int LT_BIN_BITS = VKRS_LT_BIN_BITS;
 #ifdef VKRS_LT_BINS
 constexpr int LT_BINS = VKRS_LT_BINS; // (the bin map is a multiplication: any number of bins works)
@@ -1041,7 +1049,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     LT_MARK(sm, 2);
 
     // ---- count: one shared-memory reduction per key ----
-#pragma unroll 4
+#pragma unroll LT_CP_UNROLL
     for (uint32_t p = tid; p < size; p += LT_THREADS) atomicAdd(&cnt[__umulhi(in[p] - base, mult)], 1u);
     LT_MARK(sm, 3);
     __syncthreads();
@@ -1101,7 +1109,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     //      cnt[bin] = one past the last position of the bin, cnt[bin - 1] = its first.  (`gbuf` may still hold the
     //      previous item's output until the barrier behind the count: first touched here) ----
     if (tid < 4) grouped[size + tid] = 0xFFFFFFFFu; // the fix-up reads up to three keys past its bin: never smaller than a key
-#pragma unroll 4
+#pragma unroll LT_CP_UNROLL
     for (uint32_t p = tid; p < size; p += LT_THREADS) {
         const uint32_t k = in[p];
         grouped[atomicAdd(&cnt[__umulhi(k - base, mult)], 1u)] = k;
@@ -1119,7 +1127,7 @@ __device__ __forceinline__ bool local_tile_bins(LocalTileSmem &sm, const uint32_
     // ---- fix-up, one position per thread: the bin's bounds from the counter array, the first four keys of the bin
     //      compared without a branch (a key read past the bin's end belongs to a later bin and is larger), a loop
     //      for larger bins ----
-#pragma unroll 2
+#pragma unroll LT_FIX_UNROLL
     for (uint32_t p = tid; p < size; p += LT_THREADS) {
         const uint32_t k = grouped[p];
         const uint32_t bin = __umulhi(k - base, mult);
