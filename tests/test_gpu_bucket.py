@@ -156,6 +156,42 @@ def test_big_buckets_are_counted_not_sorted(handle, dev, oracle):
     st = handle.bucket_stats()
 
 
+def test_skew_aware_ranking_loops(handle, dev, oracle):
+    """The unstable scatter picks its ranking loop per tile and warp from the FIRST round (32 keys) of the warp's
+    640-key chunk: plain atomics, "all one digit", or "hot digit" (vkrs_msd.cuh).  Chunks whose later rounds do not look
+    like the first one must come out right whichever loop was picked."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(99)
+    n = 1_920_000  # a whole number of 7680-key tiles: every tile takes the full-tile path
+    chunk = 640
+    pos = np.arange(n) % chunk
+    rnd = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    one = (np.uint32(0x5A000000) | (rnd & np.uint32(0x00FFFFFF))).astype(np.uint32)     # top digit 0x5A
+    lane = np.arange(n) % 32
+    cases = {
+        "first_round_uniform_rest_random": np.where(pos < 32, one, rnd),
+        "first_round_random_rest_uniform": np.where(pos < 32, rnd, one),
+        "first_round_hot_rest_random": np.where((pos < 32) & (lane < 12), one, rnd),        # 12 of 32 lanes on the hot digit
+        "hot_lanes_every_round": np.where(lane % 3 == 0, one, rnd),                       # 11 of 32, every round
+        "hot_digit_changes_per_chunk": np.where(lane < 20, (np.uint32(0x01000000) * ((np.arange(n) // chunk) % 256).astype(np.uint32))
+                                                | (rnd & np.uint32(0x00FFFFFF)), rnd),
+        "all_one_digit": one,
+    }
+    for name, keys in cases.items():
+        keys = keys.astype(np.uint32)
+        for schedule in (capi.SCHEDULE_BUCKET, capi.SCHEDULE_LSD_UNSTABLE_FIRST):
+            out, _ = run_sort(handle, keys, dev, schedule)
+            assert np.array_equal(out, np.sort(keys)), (name, schedule)
+    # the same through int32 keys (the typed transform is applied when a key is read from the tile)
+    ints = cases["first_round_hot_rest_random"].view(np.int32)
+    b0 = torch.from_numpy(ints.copy()).to(dev)
+    handle.set_schedule(capi.SCHEDULE_BUCKET)
+    handle.multi_sort_typed(b0, torch.empty_like(b0), None, capi.multi_push_constants(n, 32), capi.KEY_I32)
+    handle.check_device_error()
+    assert np.array_equal(b0.cpu().numpy(), np.sort(ints))
+
+
 def test_bucket_fallback_is_taken_and_correct(handle, dev, oracle):
     """More big buckets than the counting path takes (256 at 16 low bits): the device raises the fallback word and
     the stable LSD passes behind the schedule sort the array."""
