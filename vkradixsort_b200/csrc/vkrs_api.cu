@@ -605,6 +605,22 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
             VKRS_CUDA(h, launch_pdl(msd_items_kernel, dim3(MSD_SUBS / 256), dim3(256), 0, s, (const uint32_t *) w.sub_start, MSD_SUBS, n,
                                     item_first, item_lo, item_stride, w.plan, w.big));
         }
+        // buckets too large for shared memory ("big": msd_items_kernel listed them) are sorted by counting: a histogram of
+        // their low bits, then a fill.  Both kernels exit at once when there are none.  The histogram runs BEFORE the
+        // shared-memory sort: an item that fits a buffer although it holds a big bucket is sorted (and, for typed keys,
+        // mapped back) by msd_local_tile_kernel, and the histogram must see the keys as pass 2 left them.
+        {
+            constexpr size_t big_smem = (32768 + 40) * sizeof(uint32_t);
+            static thread_local int configured_device = -1;
+            if (configured_device != h->device) {
+                r = set_smem(h, msd_big_hist_kernel<XF>, big_smem);
+                if (r) return r;
+                configured_device = h->device;
+            }
+            LaunchScope scope(h, "msd_big_hist_kernel", s);
+            VKRS_CUDA(h, launch_pdl(msd_big_hist_kernel<XF>, dim3(h->sm_count), dim3(BIG_HIST_THREADS), big_smem, s, (const uint32_t *) buf0,
+                                    (const MsdPlan *) w.plan, (const BigBucket *) w.big, w.big_pool, w.big_done, w.big_vcs));
+        }
         uint32_t grid = (uint32_t) (h->sm_count * VKRS_LT_MIN_BLOCKS);
         if (XF != 0) {
             static thread_local int configured_device = -1;
@@ -631,20 +647,7 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
             VKRS_CUDA(h, launch_pdl(msd_local_redo_kernel<XF>, dim3(grid), dim3(LT_THREADS), sizeof(LocalRedoSmem), s, buf0,
                                     (const uint32_t *) w.sub_start, (const uint32_t *) item_first, (const MsdPlan *) w.plan, (const uint32_t *) redo));
         }
-        // buckets too large for shared memory ("big": msd_items_kernel listed them) are sorted by counting: a histogram of
-        // their low bits, then a fill.  Both kernels exit at once when there are none.
-        {
-            constexpr size_t big_smem = (32768 + 40) * sizeof(uint32_t);
-            static thread_local int configured_device = -1;
-            if (configured_device != h->device) {
-                r = set_smem(h, msd_big_hist_kernel<XF>, big_smem);
-                if (r) return r;
-                configured_device = h->device;
-            }
-            LaunchScope scope(h, "msd_big_hist_kernel", s);
-            VKRS_CUDA(h, launch_pdl(msd_big_hist_kernel<XF>, dim3(h->sm_count), dim3(BIG_HIST_THREADS), big_smem, s, (const uint32_t *) buf0,
-                                    (const MsdPlan *) w.plan, (const BigBucket *) w.big, w.big_pool, w.big_done, w.big_vcs));
-        }
+        // ... and the big buckets are filled from their counters last: the fill only reads the counters.
         LaunchScope scope(h, "msd_big_fill_kernel", s);
         VKRS_CUDA(h, launch_pdl(msd_big_fill_kernel<XF>, dim3(grid), dim3(512), 0, s, buf0, (const MsdPlan *) w.plan, (const BigBucket *) w.big,
                                 w.big_pool, (const uint32_t *) w.big_vcs));

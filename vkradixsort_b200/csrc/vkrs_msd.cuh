@@ -774,8 +774,15 @@ msd_items_kernel(const uint32_t *__restrict__ sub_start, uint32_t num_sub, uint3
         }
     };
     fill(w_prev + 1, w_j < last ? w_j : last, j, s_j);
-    // windows in which no bucket starts (the tail of a large last bucket), and the end marker
-    fill(j == num_sub - 1 ? w_j + 1 : 1, j == num_sub - 1 ? last + 1 : 0, num_sub, n);
+    // windows in which no bucket starts (the tail of a large last bucket) ...
+    const bool is_last = j == num_sub - 1;
+    fill(is_last ? w_j + 1 : 1, is_last ? last : 0, num_sub, n);
+    // ... and the end marker -- always: when the last buckets are empty and n is a multiple of the window, w_j is the
+    // marker's own index and the range above is empty
+    if (is_last) {
+        item_first[last + 1] = num_sub;
+        item_lo[last + 1] = n;
+    }
 }
 
 struct LocalTileSmem {
