@@ -253,7 +253,10 @@ int vkrs_get_schedule(vkrs_handle handle);
 const char *vkrs_schedule_name(int schedule);
 /* Hint for the BUCKET schedule: all keys of the following keys-only sorts lie in [lo_key, hi_key] (e.g. one
  * rank's key range after the multi-GPU exchange).  The schedule finds the occupied key range by itself; with
- * the hint its first histogram is already counted in the right digit window, which saves one 4 B/key recount.  A wrong hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint. */
+ * the hint its first histogram is already counted in the right digit window, which saves one 4 B/key recount.  A wrong
+ * hint costs that recount, never correctness.  (0, 0xFFFFFFFF) = no hint: the schedule then guesses the window from
+ * 16384 sample keys (right for keys that simply do not fill the 32 bits, e.g. the reference's 28-bit test keys,
+ * MultiRadixSort.cpp:126; environment VKRS_GUESS_WINDOW=0 turns the guess off). */
 int vkrs_set_key_span_hint(vkrs_handle handle, uint32_t lo_key, uint32_t hi_key);
 /* Control words of the handle's last BUCKET sort, for tests and diagnostics: out16 = {shift of pass 1,
  * shift of pass 2 (= low bits left to the local sort), fallback taken, histogram recounted, smallest key,

@@ -120,16 +120,38 @@ def _counting_sort(bucket: np.ndarray, value_base: int, low_bits: int) -> np.nda
     return (np.repeat(np.arange(1 << low_bits, dtype=np.int64), counts) + value_base).astype(np.uint32)
 
 
-def sort(keys: np.ndarray, seed: int = 0, hint=None, fix_up_limit: int = 200_000):
+GUESS_SAMPLES = 16384  # MSD_GUESS_SAMPLES
+
+
+def guess_window(keys: np.ndarray):
+    """msd_guess_window_kernel / msd_guess_window(): without a key-span hint the first histogram counts in the digit window
+    of 16384 evenly spread sample keys -- pushed down by an eighth of a top-level bucket, or to 0 -- unless the largest
+    sample would not fit it.  Returns (base0, shift0)."""
+    n = keys.shape[0]
+    idx = (np.arange(GUESS_SAMPLES, dtype=np.uint64) * np.uint64(n)) // np.uint64(GUESS_SAMPLES)
+    smp = keys[idx.astype(np.int64)]
+    smin, smax = int(smp.min()), int(smp.max())
+    span = smax - smin
+    top = span.bit_length() - 1 if span else 0
+    s1 = top - 7 if top >= 15 else 8
+    margin = 1 << (s1 - 3)
+    b0 = smin - margin if smin > margin else 0
+    if ((smax - b0) >> s1) >= RADIX:
+        return 0, 24
+    return b0, s1
+
+
+def sort(keys: np.ndarray, seed: int = 0, hint=None, fix_up_limit: int = 200_000, guess: bool = True):
     """The whole schedule.  Returns (sorted keys, Plan).  `fix_up_limit`: above this many keys the per-key
-    fix-up loop (pure Python) is replaced by a per-item np.sort -- the plan logic is still modelled exactly."""
+    fix-up loop (pure Python) is replaced by a per-item np.sort -- the plan logic is still modelled exactly.
+    `guess` = the sampled guess of the digit window is on (the library's default; VKRS_GUESS_WINDOW=0 turns it off)."""
     keys = np.ascontiguousarray(keys, dtype=np.uint32)
     n = keys.shape[0]
     rng = np.random.default_rng(seed)
     if n == 0:
         return keys.copy(), Plan(0, 24, 16, False, False, 0)
     kmin, kmax = int(keys.min()), int(keys.max())
-    base0, shift0 = hint_window(*hint) if hint is not None else (0, 24)
+    base0, shift0 = hint_window(*hint) if hint is not None else (guess_window(keys) if guess else (0, 24))
     base, s1, recount = window(kmin, kmax, base0, shift0)
     s2 = s1 - 8
     rel = keys.astype(np.int64) - base

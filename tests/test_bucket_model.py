@@ -42,10 +42,21 @@ def test_digit_window_and_recount(oracle):
     # full-range keys: counted at (0, 24) from the start, nothing to redo
     _, p = M.sort(oracle.generate_random(n, 1, 0xFFFFFFFF))
     assert (p.base, p.shift1, p.shift2, p.recount, p.fallback, p.big_buckets) == (0, 24, 16, False, False, 0)
-    # the reference's 28-bit keys: the window moves under bit 27, the first histogram is counted again
+    # the reference's 28-bit keys: the window moves under bit 27.  The sampled guess of the window (16384 evenly spread
+    # keys) finds it before the first histogram; without the guess the first histogram is counted again
     keys = oracle.generate_random(n, 2, 0x0FFFFFFF)
     _, p = M.sort(keys)
+    assert (p.shift1, p.shift2, p.recount, p.base) == (20, 12, False, 0)
+    _, p = M.sort(keys, guess=False)
     assert (p.shift1, p.shift2, p.recount, p.base) == (20, 12, True, int(keys.min()))
+    assert M.guess_window(keys) == (0, 20) and M.guess_window(oracle.generate_random(n, 1, 0xFFFFFFFF)) == (0, 24)
+    # a key range that does not start near 0 and nearly fills a power of two: no base the samples suggest can hold the
+    # largest key -- the guess is dropped, the recount does the job
+    assert M.guess_window((np.uint32(0xC0000000) | (oracle.generate_random(n, 9, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32)) == (0, 24)
+    # small signed integers after the sign-flip map sit around 2^31: guessed
+    ints = (np.random.default_rng(3).integers(-5000, 5001, n).astype(np.int32).view(np.uint32) ^ np.uint32(0x80000000))
+    b0, s0 = M.guess_window(ints)
+    assert s0 == 8 and b0 <= int(ints.min()) and ((int(ints.max()) - b0) >> s0) < 256
     # one rank's key range after the multi-GPU exchange: shared top bits
     keys = (np.uint32(0xC0000000) | (oracle.generate_random(n, 9, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32)
     _, p = M.sort(keys)

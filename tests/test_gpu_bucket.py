@@ -109,7 +109,7 @@ def test_bucket_stages(handle, dev, oracle):
         _, b1 = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=1)
         st = handle.bucket_stats()
         assert st["shift1"] == s1 and st["shift2"] == s1 - 8, (name, st)
-        assert st["recount"] == (1 if s1 != 24 else 0), (name, st)
+        assert st["recount"] == 0, (name, st)  # 28-bit keys: the sampled guess of the digit window saves the recount
         base = np.uint32(st["key_min"] if st["recount"] else 0)  # the digits are taken from key - base (vkrs_msd.cuh)
         d1 = ((b1 - base) >> np.uint32(s1)) & np.uint32(255)
         assert np.all(np.diff(d1.astype(np.int64)) >= 0), f"{name}: pass 1 output is not grouped by the top digit"
@@ -121,6 +121,42 @@ def test_bucket_stages(handle, dev, oracle):
         b0, _ = run_sort(handle, keys, dev, capi.SCHEDULE_BUCKET, stop=3)
         assert handle.bucket_stats()["fallback"] == 0, name
         assert oracle.test_sort(np.sort(keys), b0) == -1, f"{name}: local sort"
+
+
+def test_digit_window_guess_and_recount(dev, oracle, built_lib, monkeypatch):
+    """Without a key-span hint the first histogram counts in the digit window of 16384 sample keys (msd_guess_window_kernel);
+    with the guess off (VKRS_GUESS_WINDOW=0) or wrong, msd_window_kernel moves the window and the histogram is recounted.
+    The control words match the numpy model of the same decisions (oracle/bucket_model.py)."""
+    from oracle import bucket_model as M
+    from vkradixsort_b200 import Handle, capi
+
+    n = 300_001
+    rng = np.random.default_rng(21)
+    cases = {
+        "uniform32": oracle.generate_random(n, 1, 0xFFFFFFFF),
+        "reference28": oracle.generate_random(n, 2, 0x0FFFFFFF),
+        "bits20": oracle.generate_random(n, 3, 0x000FFFFF),
+        "rank_range": (np.uint32(0xC0000000) | (oracle.generate_random(n, 9, 0xFFFFFFFF) >> np.uint32(2))).astype(np.uint32),
+        "offset_range": (np.uint32(123456789) + rng.integers(0, 3_000_000, n, dtype=np.uint32)).astype(np.uint32),
+        "around_2^31": (np.uint32(0x7FFFF000) + rng.integers(0, 0x2000, n, dtype=np.uint32)).astype(np.uint32),
+        "all_equal": np.full(n, 0xDEADBEEF, dtype=np.uint32),
+        # the samples miss the outliers: the guess is wrong, the recount repairs it
+        "outliers": np.concatenate([oracle.generate_random(n - 2, 4, 0x00FFFFFF), np.array([0xFFFFFFF0, 0x80000000], dtype=np.uint32)]),
+    }
+    for guess in (True, False):
+        monkeypatch.setenv("VKRS_GUESS_WINDOW", "1" if guess else "0")
+        h = Handle(0, n)
+        try:
+            for name, keys in cases.items():
+                out, _ = run_sort(h, keys, dev, capi.SCHEDULE_BUCKET)
+                st = h.bucket_stats()
+                assert np.array_equal(out, np.sort(keys)), (name, guess)
+                _, p = M.sort(keys, guess=guess, fix_up_limit=0)
+                assert (st["shift1"], st["shift2"], st["recount"], st["base"]) == (p.shift1, p.shift2, int(p.recount), p.base), (name, guess, st, p)
+        finally:
+            h.close()
+    keys = cases["reference28"]
+    assert M.sort(keys, guess=True, fix_up_limit=0)[1].recount is False and M.sort(keys, guess=False, fix_up_limit=0)[1].recount is True
 
 
 def test_big_buckets_are_counted_not_sorted(handle, dev, oracle):

@@ -105,6 +105,7 @@ struct vkrs_context {
     uint32_t msd_segments_cap = 0; // segments the workspace was laid out for
     uint32_t msd_plan_n = 0, msd_plan_segments = 0, msd_plan_seg_keys = 0; // cached pass-1 piece table
     int msd_stop_after = 0; // vkrs_debug_bucket_stop: 0 = run the whole schedule
+    bool msd_guess_window = true; // VKRS_GUESS_WINDOW=0 turns the sampled guess of the digit window off (tests of the recount path)
     uint32_t msd_first_shift = 24, msd_first_base = 0; // digit window the first histogram of the bucket schedule counts in (vkrs_set_key_span_hint)
     uint32_t msd_use_bins = 1; // local sort: 0 = per-bucket path only (VKRS_LOCAL_BINS=0, tests)
     uint32_t *msd_items = nullptr; // item_first[items + 1] | item_lo[items + 1] of the local sort
@@ -569,6 +570,11 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
     const uint32_t shift0 = XF == 0 ? h->msd_first_shift : 24u; // the key-span hint is about raw keys
     r = msd_begin(h, w, n, segments, seg_keys, shift0, shift0 - 8, XF == 0 ? h->msd_first_base : 0u, s);
     if (r) return r;
+    if (n > 0 && h->msd_guess_window && (XF != 0 || (h->msd_first_shift == 24 && h->msd_first_base == 0))) {
+        // no key-span hint: guess the digit window from a sample, so that keys that do not fill the 32 bits are not counted twice
+        LaunchScope scope(h, "msd_guess_window_kernel", s);
+        VKRS_CUDA(h, launch_pdl(msd_guess_window_kernel<XF>, dim3(1), dim3(MSD_GUESS_THREADS), 0, s, (const uint32_t *) buf0, n, w.plan));
+    }
     // ---- pass 1: top digit, whole array = one bucket ----
     r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
     if (r) return r;
@@ -804,6 +810,7 @@ int vkrs_create(vkrs_handle *out_handle, int device, uint64_t max_num_elements_h
         if (iv >= 0 && iv < NUM_VARIANTS) h->variant = iv;
     }
     if (const char *v = getenv("VKRS_LOCAL_BINS")) h->msd_use_bins = atoi(v) != 0 ? 1u : 0u;
+    if (const char *v = getenv("VKRS_GUESS_WINDOW")) h->msd_guess_window = atoi(v) != 0;
     if (const char *v = getenv("VKRS_SCHEDULE")) {
         int iv = atoi(v);
         if (iv >= 0 && iv < VKRS_NUM_SCHEDULES) h->schedule = iv;
