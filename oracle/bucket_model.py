@@ -124,12 +124,16 @@ GUESS_SAMPLES = 16384  # MSD_GUESS_SAMPLES
 
 
 def guess_window(keys: np.ndarray):
-    """msd_guess_window_kernel / msd_guess_window(): without a key-span hint the first histogram counts in the digit window
-    of 16384 evenly spread sample keys -- pushed down by an eighth of a top-level bucket, or to 0 -- unless the largest
+    """msd_init_kernel / msd_guess_window(): without a key-span hint the first histogram counts in the digit window
+    of 16384 sample keys (16 blocks of 1024 consecutive keys, evenly spread, both ends of the array included) -- pushed down by an eighth of a top-level bucket, or to 0 -- unless the largest
     sample would not fit it.  Returns (base0, shift0)."""
     n = keys.shape[0]
-    idx = (np.arange(GUESS_SAMPLES, dtype=np.uint64) * np.uint64(n)) // np.uint64(GUESS_SAMPLES)
-    smp = keys[idx.astype(np.int64)]
+    t = np.arange(GUESS_SAMPLES, dtype=np.int64) % 1024          # thread
+    i = np.arange(GUESS_SAMPLES, dtype=np.int64) // 1024         # block of 1024 consecutive keys, 16 of them
+    idx = np.minimum(t, n - 1)
+    if n >= 1024:
+        idx = idx + (i * (n - 1024)) // 15
+    smp = keys[idx]
     smin, smax = int(smp.min()), int(smp.max())
     span = smax - smin
     top = span.bit_length() - 1 if span else 0

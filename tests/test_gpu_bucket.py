@@ -124,7 +124,7 @@ def test_bucket_stages(handle, dev, oracle):
 
 
 def test_digit_window_guess_and_recount(dev, oracle, built_lib, monkeypatch):
-    """Without a key-span hint the first histogram counts in the digit window of 16384 sample keys (msd_guess_window_kernel);
+    """Without a key-span hint the first histogram counts in the digit window of 16384 sample keys (msd_init_kernel);
     with the guess off (VKRS_GUESS_WINDOW=0) or wrong, msd_window_kernel moves the window and the histogram is recounted.
     The control words match the numpy model of the same decisions (oracle/bucket_model.py)."""
     from oracle import bucket_model as M

@@ -521,11 +521,14 @@ int msd_pass(vkrs_context *h, const MsdWorkspace &w, int pass, const uint32_t *i
 }
 
 // init + (cached per N) the piece table of the first pass: pieces == segments, one bucket [0, n)
+// (guess_keys != NULL: no key-span hint was given -- the init kernel guesses the digit window from a sample of these keys)
+template <int XF = 0>
 int msd_begin(vkrs_context *h, const MsdWorkspace &w, uint32_t n, uint32_t segments, uint32_t seg_keys, uint32_t shift0,
-              uint32_t shift1, uint32_t base0, cudaStream_t s) {
+              uint32_t shift1, uint32_t base0, cudaStream_t s, const uint32_t *guess_keys = nullptr) {
     {
         LaunchScope scope(h, "msd_init_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_init_kernel, dim3(1), dim3(32), 0, s, w.plan, shift0, shift1, base0));
+        VKRS_CUDA(h, launch_pdl(msd_init_kernel<XF>, dim3(1), dim3(MSD_GUESS_THREADS), 0, s, w.plan, shift0, shift1, base0, guess_keys, n,
+                                guess_keys != nullptr ? 1u : 0u));
     }
     if (h->msd_plan_n != n || h->msd_plan_segments != segments || h->msd_plan_seg_keys != seg_keys) {
         LaunchScope scope(h, "msd_plan_pieces_kernel", s);
@@ -568,13 +571,10 @@ int msd_sort_t(vkrs_context *h, uint32_t *buf0, uint32_t *buf1, uint32_t n, cuda
     if (r) return r;
     const MsdWorkspace w(h->msd_ws, h->msd_segments_cap);
     const uint32_t shift0 = XF == 0 ? h->msd_first_shift : 24u; // the key-span hint is about raw keys
-    r = msd_begin(h, w, n, segments, seg_keys, shift0, shift0 - 8, XF == 0 ? h->msd_first_base : 0u, s);
+    // no key-span hint: the digit window is guessed from a sample, so that keys that do not fill the 32 bits are not counted twice
+    const bool guess = h->msd_guess_window && (XF != 0 || (h->msd_first_shift == 24 && h->msd_first_base == 0));
+    r = msd_begin<XF>(h, w, n, segments, seg_keys, shift0, shift0 - 8, XF == 0 ? h->msd_first_base : 0u, s, guess ? (const uint32_t *) buf0 : nullptr);
     if (r) return r;
-    if (n > 0 && h->msd_guess_window && (XF != 0 || (h->msd_first_shift == 24 && h->msd_first_base == 0))) {
-        // no key-span hint: guess the digit window from a sample, so that keys that do not fill the 32 bits are not counted twice
-        LaunchScope scope(h, "msd_guess_window_kernel", s);
-        VKRS_CUDA(h, launch_pdl(msd_guess_window_kernel<XF>, dim3(1), dim3(MSD_GUESS_THREADS), 0, s, (const uint32_t *) buf0, n, w.plan));
-    }
     // ---- pass 1: top digit, whole array = one bucket ----
     r = msd_pass<XF>(h, w, 0, buf0, buf1, n, ctas, segments, nullptr, nullptr, 0, true, nullptr, true, false, s);
     if (r) return r;

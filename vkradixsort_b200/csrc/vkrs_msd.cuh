@@ -105,27 +105,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32
     return r;
 }
 
-// Start of a sort: where the first histogram counts (base 0, top byte unless a key-span hint says otherwise), flags down.
-__global__ void msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1, uint32_t base0) {
-    grid_dependency_wait();
-    if (threadIdx.x == 0) {
-        plan->shift[0] = shift0;
-        plan->shift[1] = shift1;
-        plan->base = base0;
-        plan->fallback = 0;
-        plan->recount = 0;
-        plan->key_min = 0xFFFFFFFFu;
-        plan->key_max = 0;
-        plan->max_sub = 0;
-        plan->skip_pass2 = 0;
-        plan->num_big = 0;
-        plan->big_items = 0;
-        plan->num_redo = 0;
-    }
-}
-
 // Before the first histogram (only when the caller gave no key-span hint): a guess of the digit window from MSD_GUESS_SAMPLES
-// keys spread evenly over the array, so that keys which do not fill the 32 bits -- the reference's own 28-bit test keys
+// keys -- 16 blocks of 1024 keys spread evenly over the array --, so that keys which do not fill the 32 bits -- the reference's own 28-bit test keys
 // (MultiRadixSort.cpp:126), small non-negative integers -- are counted in their final window at once instead of being
 // counted again (+60 us at 10^8 keys).  The guess is the window of the samples' range, pushed down by an eighth of a
 // top-level bucket (the true smallest key lies a little below the smallest sample) or to 0; it is dropped if the
@@ -144,37 +125,59 @@ __host__ __device__ __forceinline__ bool msd_guess_window(uint32_t smin, uint32_
     base0 = b0;
     return true;
 }
+// Start of a sort: flags down, and where the first histogram counts -- (base0, shift0) as the caller's key-span hint says
+// (default: base 0, top byte), or, with `guess` set, the window guessed from the sample keys (see above; part of this
+// kernel rather than one of its own: every kernel in front of the first histogram is a link of ~3 us in the launch chain).
 template <int XF>
 __global__ void __launch_bounds__(MSD_GUESS_THREADS)
-msd_guess_window_kernel(const uint32_t *__restrict__ keys, uint32_t n, MsdPlan *plan) {
+msd_init_kernel(MsdPlan *plan, uint32_t shift0, uint32_t shift1, uint32_t base0, const uint32_t *__restrict__ keys, uint32_t n, uint32_t guess) {
     __shared__ uint32_t red[2][MSD_GUESS_THREADS / 32];
     const uint32_t tid = threadIdx.x;
     grid_dependency_wait();
-    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    if (guess != 0 && n != 0) { // (uniform over the CTA)
+        uint32_t lo = 0xFFFFFFFFu, hi = 0;
 #pragma unroll
-    for (int i = 0; i < MSD_GUESS_SAMPLES / MSD_GUESS_THREADS; ++i) {
-        const uint32_t j = tid + i * MSD_GUESS_THREADS;                                  // sample j of MSD_GUESS_SAMPLES
-        const uint32_t idx = (uint32_t) (((uint64_t) j * n) / MSD_GUESS_SAMPLES);         // < n
-        const uint32_t k = KeyXform<uint32_t, XF>::fwd(__ldg(keys + idx));
-        lo = min(lo, k);
-        hi = max(hi, k);
-    }
-    lo = __reduce_min_sync(0xffffffffu, lo);
-    hi = __reduce_max_sync(0xffffffffu, hi);
-    if ((tid & 31) == 0) {
-        red[0][tid >> 5] = lo;
-        red[1][tid >> 5] = hi;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        lo = __reduce_min_sync(0xffffffffu, red[0][tid]);
-        hi = __reduce_max_sync(0xffffffffu, red[1][tid]);
-        uint32_t shift0, base0;
-        if (tid == 0 && msd_guess_window(lo, hi, shift0, base0)) {
-            plan->shift[0] = shift0;
-            plan->shift[1] = shift0 - 8u;
-            plan->base = base0;
+        for (int i = 0; i < MSD_GUESS_SAMPLES / MSD_GUESS_THREADS; ++i) {
+            // 16 blocks of 1024 consecutive keys, the first at the start and the last at the end of the array: coalesced
+            // reads from 16 places (16384 single keys spread over the array cost 9 us instead of 3: a page walk each)
+            uint32_t idx = tid < n ? tid : n - 1u;
+            if (n >= (uint32_t) MSD_GUESS_THREADS)
+                idx += (uint32_t) (((uint64_t) i * (n - MSD_GUESS_THREADS)) / (MSD_GUESS_SAMPLES / MSD_GUESS_THREADS - 1));
+            const uint32_t k = KeyXform<uint32_t, XF>::fwd(__ldg(keys + idx));
+            lo = min(lo, k);
+            hi = max(hi, k);
         }
+        lo = __reduce_min_sync(0xffffffffu, lo);
+        hi = __reduce_max_sync(0xffffffffu, hi);
+        if ((tid & 31) == 0) {
+            red[0][tid >> 5] = lo;
+            red[1][tid >> 5] = hi;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            lo = __reduce_min_sync(0xffffffffu, red[0][tid]);
+            hi = __reduce_max_sync(0xffffffffu, red[1][tid]);
+            uint32_t gs = 0, gb = 0;
+            if (msd_guess_window(lo, hi, gs, gb)) {
+                shift0 = gs;
+                shift1 = gs - 8u;
+                base0 = gb;
+            }
+        }
+    }
+    if (tid == 0) {
+        plan->shift[0] = shift0;
+        plan->shift[1] = shift1;
+        plan->base = base0;
+        plan->fallback = 0;
+        plan->recount = 0;
+        plan->key_min = 0xFFFFFFFFu;
+        plan->key_max = 0;
+        plan->max_sub = 0;
+        plan->skip_pass2 = 0;
+        plan->num_big = 0;
+        plan->big_items = 0;
+        plan->num_redo = 0;
     }
 }
 
